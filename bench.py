@@ -1,0 +1,412 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the BT.709 4:2:0 -> sRGB BGRA8 decode path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                    [--workload c2_1080p|c3_uhd|c2_rescale|c4_alpha|c5_encode] [--gamma bt709|apple|srgb|linear]
+
+Metric (BASELINE.json): Gpix/s of BT.709 4:2:0 -> sRGB BGRA8, plus % of the HBM roofline.
+A "step" is one pass of the hot path over one resident batch of synthetic frames (configs[1]:
+600 x 1920x1080 per GPU, 1.87 GB in / 4.98 GB out, far larger than the 126 MB L2, so no flush is
+needed between steps).  `value` counts pixels of all ranks / max-over-ranks device time.
+Multi-GPU: one process per GPU (torchrun), frames sharded by index, no data-path collective;
+torch.distributed is used only for the barrier and for reducing the timing scalars.
+
+`e2e` is the same metric through the reference-facing host API (MetalBT709Decoder_decodeBT709
+with pinned HOST buffers): upload, kernel and read-back are all inside the timed region.
+
+--impl reference times the reference's own CPU implementation of the path (oracle/_ref: the
+unmodified BT709.h compiled where it lies; else the oracle port) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (w, h, frames per GPU, kind)
+    "c2_1080p": (1920, 1080, 600, "decode"),
+    "c3_uhd": (3840, 2160, 300, "decode"),       # 2400 frames / 8 GPUs per BASELINE configs[2]
+    "c2_rescale": (1920, 1080, 200, "rescale"),  # pass 2 alone, 1080p -> 2560x1440
+    "c2_twopass": (1920, 1080, 200, "twopass"),  # decode -> intermediate -> rescale
+    "c4_alpha": (2048, 1536, 200, "alpha"),
+    "c5_encode": (2048, 1536, 200, "encode"),
+}
+GAMMAS = {"apple": 0, "srgb": 1, "linear": 2, "bt709": 3}
+
+
+def _dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic(kind):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(kind)
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------- CPU reference
+def _cpu_decode_frames(gamma, w, h, nframes, threads):
+    """Decode `nframes` synthetic 1080p-class frames with the reference's CPU code on `threads`
+    host threads (one frame per task).  Returns (seconds, kind)."""
+    import ctypes
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from _oracle import Oracle, frame_random, ref_oracle
+    ref = ref_oracle()
+    kind = "reference" if ref is not None else "port"
+    impl = ref if ref is not None else Oracle()
+    frames = [frame_random(w, h, seed=709 + i) for i in range(min(nframes, 4))]
+    idx = iter(range(nframes))
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                i = next(idx, None)
+            if i is None:
+                return
+            y, c = frames[i % len(frames)]
+            if kind == "reference":
+                impl.decode_nv12(gamma, y, c)
+            else:
+                impl.decode_nv12(gamma, y, c, nthreads=1)
+
+    ths = [threading.Thread(target=work) for _ in range(threads)]
+    t0 = time.perf_counter()
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return time.perf_counter() - t0, kind
+
+
+def cpu_baseline(gamma, w, h, budget_core_s=16.0):
+    cores = os.cpu_count() or 1
+    # ~0.4 core-seconds per 1080p frame with a transfer curve, ~0.09 without
+    per_frame = (0.42 if gamma != 1 else 0.09) * (w * h) / (1920 * 1080)
+    nframes = max(cores, int(budget_core_s * max(1, cores // 8) / per_frame))
+    nframes = min(nframes, cores * 8)
+    secs, kind = _cpu_decode_frames(gamma, w, h, nframes, cores)
+    return {"value": nframes * w * h / secs / 1e9, "unit": "Gpix/s", "cores": cores, "kind": kind,
+            "sample": f"{nframes} synthetic {w}x{h} frames, one frame per task on {cores} host threads"}, secs
+
+
+def run_reference(args):
+    rank, _, world = _dist_env()
+    if rank != 0:
+        return 0
+    w, h, frames, kind = WORKLOADS[args.workload]
+    gamma = GAMMAS[args.gamma]
+    cores = os.cpu_count() or 1
+    per_step = max(cores, min(cores * 2, 256))
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        _cpu_decode_frames(gamma, w, h, max(1, cores // 2), cores)
+    t = 0.0
+    kind_impl = "port"
+    for _ in range(args.steps):
+        s, kind_impl = _cpu_decode_frames(gamma, w, h, per_step, cores)
+        t += s
+    value = per_step * args.steps * w * h / t / 1e9
+    sample = f"{per_step} synthetic {w}x{h} frames per step, one frame per task on {cores} host threads"
+    line = {
+        "impl": "reference", "metric": "Gpix/s BT.709 4:2:0->sRGB BGRA8", "value": value, "unit": "Gpix/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (double pow), u8 I/O",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w}x{h} NV12 video-range -> sRGB BGRA8, gamma={args.gamma}",
+                   "frames_per_step": per_step, "note": "reference CPU path on host cores; bounded sample"},
+        "cpu_baseline": {"value": value, "unit": "Gpix/s", "cores": cores, "kind": kind_impl, "sample": sample},
+        "e2e": {"value": value, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def make_batch(torch, w, h, frames, seed, kind):
+    """F-random synthetic frames generated on the device: Y~U{16..235}, Cb,Cr~U{16..240}."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    d = {}
+    if kind in ("decode", "alpha", "twopass"):
+        d["y"] = torch.randint(16, 236, (frames, h, w), dtype=torch.uint8, device="cuda", generator=g)
+        d["c"] = torch.randint(16, 241, (frames, h // 2, w), dtype=torch.uint8, device="cuda", generator=g)
+        d["out"] = torch.empty((frames, h, w, 4), dtype=torch.uint8, device="cuda")
+    if kind == "alpha":
+        d["a"] = torch.randint(16, 236, (frames, h, w), dtype=torch.uint8, device="cuda", generator=g)
+    if kind in ("rescale", "twopass"):
+        if kind == "rescale":
+            d["src"] = torch.randint(0, 256, (frames, h, w, 4), dtype=torch.uint8, device="cuda", generator=g)
+        d["big"] = torch.empty((frames, 1440, 2560, 4), dtype=torch.uint8, device="cuda")
+    if kind == "encode":
+        d["src"] = torch.randint(0, 256, (frames, h, w, 4), dtype=torch.uint8, device="cuda", generator=g)
+        d["y"] = torch.empty((frames, h, w), dtype=torch.uint8, device="cuda")
+        d["c"] = torch.empty((frames, h // 2, w), dtype=torch.uint8, device="cuda")
+    return d
+
+
+def algorithmic_bytes(kind, w, h, frames):
+    px = w * h * frames
+    if kind == "decode":
+        return 5.5 * px
+    if kind == "alpha":
+        return 6.5 * px
+    if kind == "encode":
+        return 5.5 * px
+    if kind == "rescale":
+        return 4.0 * px + 4.0 * 2560 * 1440 * frames
+    if kind == "twopass":
+        return 5.5 * px + 4.0 * px + 4.0 * 2560 * 1440 * frames
+    raise ValueError(kind)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import metalbt709decoder_b200 as pkg
+    from metalbt709decoder_b200.sharding import frame_slice, gather_job_stats
+
+    rank, local_rank, world = _dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    w, h, frames_per_gpu, kind = WORKLOADS[args.workload]
+    if args.frames:
+        frames_per_gpu = args.frames
+    gamma = GAMMAS[args.gamma]
+    if kind == "alpha":
+        gamma = 1
+    lo, hi = frame_slice(frames_per_gpu * world, rank, world)  # weak scaling: fixed frames per GPU
+    frames = hi - lo
+    ctx = pkg.BT709Context(local_rank)
+    d = make_batch(torch, w, h, frames, 709 + lo, kind)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        if kind == "decode":
+            ctx.decode_nv12(gamma, d["y"], d["c"], d["out"], stream=stream)
+        elif kind == "alpha":
+            ctx.decode_nv12(gamma, d["y"], d["c"], d["out"], alpha_y=d["a"], stream=stream)
+        elif kind == "rescale":
+            ctx.rescale_bgra(d["src"], d["big"], stream=stream)
+        elif kind == "twopass":
+            ctx.decode_rescale_nv12(gamma, d["y"], d["c"], d["out"], d["big"], stream=stream)
+        elif kind == "encode":
+            ctx.encode_bgra_to_nv12(1, 0, d["src"], d["y"], d["c"], stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = ctx.launch_count
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    evs[0].record(stream)
+    for i in range(args.steps):
+        step()
+        evs[i + 1].record(stream)
+    barrier()
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = evs[0].elapsed_time(evs[-1])
+    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    units = float(frames) * w * h * args.steps
+    secs, all_units = gather_job_stats(total_ms / 1e3, units)
+
+    # ---- end-to-end through the reference-facing host API (host buffers, copies timed)
+    e2e = None
+    if kind == "decode" and not args.no_e2e:
+        e2e = run_e2e(args, local_rank, w, h, frames, gamma)
+        if world > 1:
+            e_secs, e_units = gather_job_stats(e2e["_secs"], e2e["_units"])
+        else:
+            e_secs, e_units = e2e["_secs"], e2e["_units"]
+        e2e = {"value": e_units / e_secs / 1e9, "unit": "Gpix/s", "h2d_bytes_per_step": e2e["h2d"],
+               "d2h_bytes_per_step": e2e["d2h"], "frames_per_step": e2e["frames"], "steps": e2e["steps"],
+               "api": "MetalBT709Decoder_decodeBT709 (pinned host NV12 in, pinned host BGRA out, 4-deep stream ring)"}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        avg_launch_s = (sum(per_launch_ms) / len(per_launch_ms)) / 1e3
+        launches_per_step = max(1, launches // max(1, args.steps))
+        ach = algorithmic_bytes(kind, w, h, frames) / avg_launch_s / 1e9
+        cpu = cpu_baseline(gamma, w, h)[0] if world == 1 else None
+        line = {
+            "metric": "Gpix/s BT.709 4:2:0->sRGB BGRA8", "value": all_units / secs / 1e9, "unit": "Gpix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": secs / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 math, u8 I/O",
+            "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {frames} x {w}x{h} NV12 video-range frames per GPU -> sRGB BGRA8 "
+                                   f"({kind}), gamma={args.gamma if kind != 'alpha' else 'srgb'}",
+                       "frames_per_gpu": frames, "l2": "inputs+outputs per step >> 126 MB L2; no flush needed",
+                       "fps": all_units / (w * h) / secs, "parallelism": f"frame-sharded x{world}, no collective"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "traffic": ncu_traffic(kind), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algorithmic_bytes(kind, w, h, frames) / launches_per_step,
+                         "avg_launch_ms": avg_launch_s * 1e3, "kernels_per_step": launches_per_step},
+            "cpu_baseline": cpu,
+            "e2e": e2e if e2e else {"value": None, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                    "note": "e2e is measured on the decode workloads"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, device, w, h, frames, gamma):
+    """Per-frame calls of the reference-facing host API with pinned host buffers."""
+    import numpy as np
+    from metalbt709decoder_b200 import renderer as R
+    import torch
+    tf = {0: R.kMBDTransferFunction_ITU_R_709_2, 1: R.kMBDTransferFunction_sRGB, 2: R.kMBDTransferFunction_Linear}
+    mg = gamma if gamma in (0, 1, 2) else 0  # the ObjC-facing decoder exposes the Metal gammas (Apple default)
+    mrc = R.MetalRenderContext(device)
+    assert mrc.setupMetal()
+    dec = R.MetalBT709Decoder()
+    dec.metalRenderContext = mrc
+    dec.gamma = mg
+    ring = 16
+    rng = np.random.default_rng(709)
+    bufs, texs = [], []
+    for i in range(ring):
+        pb = R.BGRAToBT709Converter.createCoreVideoYCbCrBuffer(w, h)
+        pb.y[:] = rng.integers(16, 236, (h, w), dtype=np.uint8)
+        pb.cbcr[:] = rng.integers(16, 241, (h // 2, w), dtype=np.uint8)
+        pb.setAttachments(R.kMBDYCbCrMatrix_ITU_R_709_2, tf[mg])
+        bufs.append(pb)
+        texs.append(mrc.makeBGRATexture(w, h))
+    n = min(frames, 200)
+    steps = 3
+
+    def one_pass():
+        for i in range(n):
+            ok = dec.decodeBT709(bufs[i % ring], None, texs[i % ring], None, w, h, False)
+            assert ok
+        assert mrc.waitUntilCompleted()
+
+    one_pass()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one_pass()
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    out = {"_secs": secs, "_units": float(n) * w * h * steps, "h2d": int(n * w * h * 1.5), "d2h": n * w * h * 4,
+           "frames": n, "steps": steps}
+    for b in bufs:
+        b.release()
+    for t in texs:
+        t.release()
+    dec.release()
+    mrc.release()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2_1080p", choices=sorted(WORKLOADS))
+    ap.add_argument("--gamma", default="bt709", choices=sorted(GAMMAS))
+    ap.add_argument("--frames", type=int, default=0, help="override frames per GPU")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,331 @@
+// bt709_api.cu — the C ABI of include/bt709_b200.h: context, argument validation, dispatch.
+//
+// Mirrors the guard clauses of -[MetalBT709Decoder processBT709ToSRGB:] (MetalBT709Decoder.m:
+// 252-492), +[BGRAToBT709Converter convert:] (BGRAToBT709Converter.m:33-57) and
+// cvpbu_ycbcr_subsample (CVPixelBufferUtils.h:275-276) as returned status codes.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/bt709_b200.h"
+#include "bt709_kernels.cuh"
+#include "bt709_tables.h"
+
+using namespace bt709;
+
+struct bt709_ctx {
+  int device = -1;
+  int sm_count = 148;
+  mutable std::atomic<int> last_cuda_error{0};
+  mutable std::atomic<unsigned long long> launches{0};
+  void *dev_blob = nullptr;  // one allocation holding every table below
+  // decode: matrix output -> sRGB byte, per bt709_gamma
+  const uint32_t *dec_lut[4] = {};
+  float dec_clamp[4] = {};
+  int dec_cells[4] = {};
+  // BT709_from_linear: linear float -> byte in gamma g (g = APPLE, SRGB, LINEAR)
+  const uint32_t *fl_lut[3] = {};
+  float fl_clamp[3] = {};
+  int fl_cells[3] = {};
+  const float *lin256[3] = {};       // BT709_tolinearNorm per input gamma
+  const float *compn256[3][3] = {};  // [gin][gout] unorm8(from_linear(to_linear(b)))
+  const float *enc444_apple = nullptr;
+  MatrixConsts m;
+};
+
+namespace {
+
+struct BlobBuilder {
+  std::vector<uint32_t> words;
+  size_t add(const void *src, size_t nwords) {
+    size_t off = (words.size() + 3) & ~size_t(3);  // 16-byte aligned sub-tables
+    words.resize(off + nwords);
+    std::memcpy(&words[off], src, nwords * 4);
+    return off;
+  }
+};
+
+int cuda_fail(const bt709_ctx *ctx, cudaError_t e) {
+  if (ctx) ctx->last_cuda_error.store((int) e);
+  return BT709_E_CUDA;
+}
+
+bool plane_ok(const bt709_plane *p) { return p && p->ptr; }
+
+// pitch >= row bytes; frame_stride >= rows * pitch when more than one frame
+int check_plane(const bt709_plane *p, size_t row_bytes, size_t rows, int nframes) {
+  if (p->pitch < row_bytes) return BT709_E_PITCH;
+  if (nframes > 1 && p->frame_stride < (rows - 1) * p->pitch + row_bytes) return BT709_E_PITCH;
+  return BT709_OK;
+}
+
+int finish(const bt709_ctx *ctx, int launch_err, void *stream, int wait) {
+  if (launch_err) return cuda_fail(ctx, (cudaError_t) launch_err);
+  ctx->launches.fetch_add(1);
+  if (wait) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t) stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e);
+  }
+  return BT709_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+    if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    if (prev == dev) prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int bt709_ctx_create(int device, bt709_ctx **out) {
+  if (!out) return BT709_E_NULL;
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    // no CPU fallback: without a CUDA device the library refuses to work
+    cudaGetLastError();
+    return BT709_E_CUDA;
+  }
+  bt709_ctx *ctx = new (std::nothrow) bt709_ctx();
+  if (!ctx) return BT709_E_NULL;
+  ctx->device = device;
+  ctx->m = matrix_consts();
+  DeviceGuard guard(device);
+  if (!guard.ok) { delete ctx; return BT709_E_CUDA; }
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) { delete ctx; return BT709_E_CUDA; }
+  ctx->sm_count = prop.multiProcessorCount;
+
+  // ---- build every table on the host, once
+  BlobBuilder blob;
+  size_t off_dec[4], off_fl[3], off_lin[3], off_comp[3][3], off_e444;
+  for (int g = 0; g < 4; g++) {
+    StepFn fn;
+    CellLut lut;
+    if (!build_step_fn(decode_code, g, &fn)) { delete ctx; return BT709_E_GAMMA; }
+    // fixed sizes so that the fast kernel has two instantiations: 2^10 cells x 32 replicas for
+    // the Apple/sRGB/BT.709 curves, 2^12 cells x 8 replicas for the steep Linear (pure sRGB
+    // encode) curve; both take 128 KB of shared memory
+    const int n = (g == kLinear) ? 12 : 10;
+    if (!build_cell_lut(fn, n, &lut)) { delete ctx; return BT709_E_GAMMA; }
+    ctx->dec_clamp[g] = lut.clamp_lo;
+    ctx->dec_cells[g] = n;
+    off_dec[g] = blob.add(lut.entries.data(), lut.entries.size());
+  }
+  for (int g = 0; g < 3; g++) {
+    StepFn fn;
+    CellLut lut;
+    if (!build_step_fn(from_linear_code, g, &fn)) { delete ctx; return BT709_E_GAMMA; }
+    int n = build_cell_lut_auto(fn, 8, 14, &lut);
+    if (n < 0) { delete ctx; return BT709_E_GAMMA; }
+    ctx->fl_clamp[g] = lut.clamp_lo;
+    ctx->fl_cells[g] = n;
+    off_fl[g] = blob.add(lut.entries.data(), lut.entries.size());
+    float lin[256];
+    for (int b = 0; b < 256; b++) lin[b] = to_linear(g, b);
+    off_lin[g] = blob.add(lin, 256);
+  }
+  for (int gi = 0; gi < 3; gi++)
+    for (int go = 0; go < 3; go++) {
+      float t[256];
+      for (int b = 0; b < 256; b++) t[b] = from_linear_code(go, to_linear(gi, b)) * (1.0f / 255.0f);
+      off_comp[gi][go] = blob.add(t, 256);
+    }
+  {
+    float t[256];  // Apple196_from_sRGB_convertRGBToYCbCr front half, BT709.h:771-808
+    for (int b = 0; b < 256; b++) t[b] = apple_oetf(srgb_eotf(b * (1.0f / 255.0f)));
+    off_e444 = blob.add(t, 256);
+  }
+
+  if ((e = cudaMalloc(&ctx->dev_blob, blob.words.size() * 4)) != cudaSuccess) { delete ctx; return BT709_E_CUDA; }
+  if ((e = cudaMemcpy(ctx->dev_blob, blob.words.data(), blob.words.size() * 4, cudaMemcpyHostToDevice)) != cudaSuccess) {
+    cudaFree(ctx->dev_blob);
+    delete ctx;
+    return BT709_E_CUDA;
+  }
+  const uint32_t *base = (const uint32_t *) ctx->dev_blob;
+  for (int g = 0; g < 4; g++) ctx->dec_lut[g] = base + off_dec[g];
+  for (int g = 0; g < 3; g++) {
+    ctx->fl_lut[g] = base + off_fl[g];
+    ctx->lin256[g] = (const float *) (base + off_lin[g]);
+    for (int go = 0; go < 3; go++) ctx->compn256[g][go] = (const float *) (base + off_comp[g][go]);
+  }
+  ctx->enc444_apple = (const float *) (base + off_e444);
+  int ke = kernels_init();
+  if (ke) {
+    cudaFree(ctx->dev_blob);
+    delete ctx;
+    return BT709_E_CUDA;
+  }
+  *out = ctx;
+  return BT709_OK;
+}
+
+void bt709_ctx_destroy(bt709_ctx *ctx) {
+  if (!ctx) return;
+  {
+    DeviceGuard guard(ctx->device);
+    if (ctx->dev_blob) cudaFree(ctx->dev_blob);
+  }
+  delete ctx;
+}
+
+int bt709_ctx_device(const bt709_ctx *ctx) { return ctx ? ctx->device : -1; }
+int bt709_last_cuda_error(const bt709_ctx *ctx) { return ctx ? ctx->last_cuda_error.load() : 0; }
+unsigned long long bt709_launch_count(const bt709_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
+
+const char *bt709_status_string(int s) {
+  switch (s) {
+    case BT709_OK: return "ok";
+    case BT709_E_NULL: return "null context, plane or pointer";
+    case BT709_E_DIMS: return "bad dimensions (non-positive, or odd on the 4:2:0 encode)";
+    case BT709_E_PITCH: return "pitch or frame stride too small, or BGRA plane not 4-byte aligned";
+    case BT709_E_GAMMA: return "unsupported gamma for this entry point";
+    case BT709_E_ALPHA_MODE: return "alpha stream requires BT709_GAMMA_SRGB";
+    case BT709_E_CUDA: return "CUDA error (see bt709_last_cuda_error)";
+    case BT709_E_SCRATCH: return "two-pass decode+rescale needs an intermediate plane";
+    default: return "unknown status";
+  }
+}
+
+int bt709_decode_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y, const bt709_plane *cbcr,
+                      const bt709_plane *alpha_y, const bt709_plane *bgra_out, int w, int h, int nframes,
+                      void *stream, int wait) {
+  if (!ctx || !plane_ok(y) || !plane_ok(cbcr) || !plane_ok(bgra_out)) return BT709_E_NULL;
+  if (alpha_y && !alpha_y->ptr) return BT709_E_NULL;
+  if (w <= 0 || h <= 0 || nframes <= 0) return BT709_E_DIMS;
+  if ((int) gamma < 0 || (int) gamma > 3) return BT709_E_GAMMA;
+  if (alpha_y && gamma != BT709_GAMMA_SRGB) return BT709_E_ALPHA_MODE;
+  const size_t cw2 = (size_t) ((w + 1) / 2) * 2, ch = (size_t) (h + 1) / 2;
+  int rc;
+  if ((rc = check_plane(y, w, h, nframes))) return rc;
+  if ((rc = check_plane(cbcr, cw2, ch, nframes))) return rc;
+  if ((rc = check_plane(bgra_out, (size_t) w * 4, h, nframes))) return rc;
+  if (alpha_y && (rc = check_plane(alpha_y, w, h, nframes))) return rc;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
+  DecodeArgs a{};
+  a.y = (const uint8_t *) y->ptr; a.py = (long long) y->pitch; a.sy = (long long) y->frame_stride;
+  a.c = (const uint8_t *) cbcr->ptr; a.pc = (long long) cbcr->pitch; a.sc = (long long) cbcr->frame_stride;
+  a.out = (uint8_t *) bgra_out->ptr; a.po = (long long) bgra_out->pitch; a.so = (long long) bgra_out->frame_stride;
+  if (alpha_y) { a.a = (const uint8_t *) alpha_y->ptr; a.pa = (long long) alpha_y->pitch; a.sa = (long long) alpha_y->frame_stride; }
+  a.w = w; a.h = h; a.nframes = nframes;
+  a.lut = ctx->dec_lut[gamma]; a.clamp_lo = ctx->dec_clamp[gamma]; a.cells_log2 = ctx->dec_cells[gamma];
+  a.m = ctx->m;
+  return finish(ctx, launch_decode(a, ctx->sm_count, stream), stream, wait);
+}
+
+int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, int in_h, const bt709_plane *out,
+                       int out_w, int out_h, int nframes, void *stream, int wait) {
+  if (!ctx || !plane_ok(in) || !plane_ok(out)) return BT709_E_NULL;
+  if (in_w <= 0 || in_h <= 0 || out_w <= 0 || out_h <= 0 || nframes <= 0) return BT709_E_DIMS;
+  int rc;
+  if ((rc = check_plane(in, (size_t) in_w * 4, in_h, nframes))) return rc;
+  if ((rc = check_plane(out, (size_t) out_w * 4, out_h, nframes))) return rc;
+  // BGRA pixels are read and written as 32-bit words
+  if (((uintptr_t) in->ptr | in->pitch | in->frame_stride | (uintptr_t) out->ptr | out->pitch | out->frame_stride) & 3)
+    return BT709_E_PITCH;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
+  RescaleArgs a{};
+  a.in = (const uint8_t *) in->ptr; a.pi = (long long) in->pitch; a.si = (long long) in->frame_stride;
+  a.out = (uint8_t *) out->ptr; a.po = (long long) out->pitch; a.so = (long long) out->frame_stride;
+  a.iw = in_w; a.ih = in_h; a.ow = out_w; a.oh = out_h; a.nframes = nframes;
+  a.scale_x = (float) in_w / (float) out_w;
+  a.scale_y = (float) in_h / (float) out_h;
+  a.lin256 = ctx->lin256[kSrgb];
+  a.enc_lut = ctx->fl_lut[kSrgb]; a.enc_clamp_lo = ctx->fl_clamp[kSrgb]; a.enc_cells_log2 = ctx->fl_cells[kSrgb];
+  return finish(ctx, launch_rescale(a, ctx->sm_count, stream), stream, wait);
+}
+
+int bt709_decode_rescale_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y, const bt709_plane *cbcr,
+                              const bt709_plane *alpha_y, const bt709_plane *scratch, const bt709_plane *bgra_out,
+                              int w, int h, int out_w, int out_h, int nframes, void *stream, int wait) {
+  // AAPLRenderer.m:891-894: exact size -> one pass straight into the destination
+  if (out_w == w && out_h == h)
+    return bt709_decode_nv12(ctx, gamma, y, cbcr, alpha_y, bgra_out, w, h, nframes, stream, wait);
+  if (!ctx) return BT709_E_NULL;
+  if (!scratch || !scratch->ptr) return BT709_E_SCRATCH;
+  // AAPLRenderer.m:940-977: decode into the same-size sRGB intermediate, then rescale
+  int rc = bt709_decode_nv12(ctx, gamma, y, cbcr, alpha_y, scratch, w, h, nframes, stream, 0);
+  if (rc) return rc;
+  return bt709_rescale_bgra(ctx, scratch, w, h, bgra_out, out_w, out_h, nframes, stream, wait);
+}
+
+int bt709_encode_bgra_to_nv12(const bt709_ctx *ctx, bt709_gamma gin, bt709_gamma gout, const bt709_plane *in,
+                              const bt709_plane *y, const bt709_plane *cbcr, int w, int h, int nframes, void *stream,
+                              int wait) {
+  if (!ctx || !plane_ok(in) || !plane_ok(y) || !plane_ok(cbcr)) return BT709_E_NULL;
+  if (w <= 0 || h <= 0 || nframes <= 0 || (w & 1) || (h & 1)) return BT709_E_DIMS;
+  if ((int) gin < 0 || (int) gin > 2 || (int) gout < 0 || (int) gout > 2) return BT709_E_GAMMA;
+  int rc;
+  if ((rc = check_plane(in, (size_t) w * 4, h, nframes))) return rc;
+  if ((rc = check_plane(y, w, h, nframes))) return rc;
+  if ((rc = check_plane(cbcr, w, h / 2, nframes))) return rc;
+  if (((uintptr_t) in->ptr | in->pitch | in->frame_stride) & 3) return BT709_E_PITCH;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
+  EncodeArgs a{};
+  a.in = (const uint8_t *) in->ptr; a.pi = (long long) in->pitch; a.si = (long long) in->frame_stride;
+  a.y = (uint8_t *) y->ptr; a.py = (long long) y->pitch; a.sy = (long long) y->frame_stride;
+  a.c = (uint8_t *) cbcr->ptr; a.pc = (long long) cbcr->pitch; a.sc = (long long) cbcr->frame_stride;
+  a.w = w; a.h = h; a.nframes = nframes;
+  a.lin256 = ctx->lin256[gin];
+  a.compn256 = ctx->compn256[gin][gout];
+  a.out_lut = ctx->fl_lut[gout]; a.out_clamp_lo = ctx->fl_clamp[gout]; a.out_cells_log2 = ctx->fl_cells[gout];
+  return finish(ctx, launch_encode(a, ctx->sm_count, stream), stream, wait);
+}
+
+int bt709_convert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t *out, int w, int h, void *stream,
+                            int wait) {
+  if (!ctx || !in || !out) return BT709_E_NULL;
+  if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) return BT709_E_DIMS;  // BGRAToBT709Converter.m:41-46
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
+  Packed444Args a{};
+  a.in = in; a.out = out; a.n = (long long) w * h; a.enc256 = ctx->enc444_apple; a.m = ctx->m;
+  return finish(ctx, launch_convert444(a, stream), stream, wait);
+}
+
+int bt709_unconvert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t *out, int w, int h, void *stream,
+                              int wait) {
+  if (!ctx || !in || !out) return BT709_E_NULL;
+  if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) return BT709_E_DIMS;  // BGRAToBT709Converter.m:69-74
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
+  Packed444Args a{};
+  a.in = in; a.out = out; a.n = (long long) w * h; a.m = ctx->m;
+  a.lut = ctx->dec_lut[kApple]; a.clamp_lo = ctx->dec_clamp[kApple]; a.cells_log2 = ctx->dec_cells[kApple];
+  return finish(ctx, launch_unconvert444(a, stream), stream, wait);
+}
+
+int bt709_copy_packed444_to_nv12(const bt709_ctx *ctx, const uint32_t *in, const bt709_plane *y,
+                                 const bt709_plane *cbcr, int w, int h, void *stream, int wait) {
+  if (!ctx || !in || !plane_ok(y) || !plane_ok(cbcr)) return BT709_E_NULL;
+  if (w <= 0 || h <= 0) return BT709_E_DIMS;
+  int rc;
+  if ((rc = check_plane(y, w, h, 1))) return rc;
+  if ((rc = check_plane(cbcr, (size_t) ((w + 1) / 2) * 2, (h + 1) / 2, 1))) return rc;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
+  CopyPackedArgs a{};
+  a.in = in; a.y = (uint8_t *) y->ptr; a.py = (long long) y->pitch; a.c = (uint8_t *) cbcr->ptr;
+  a.pc = (long long) cbcr->pitch; a.w = w; a.h = h;
+  return finish(ctx, launch_copy_packed(a, stream), stream, wait);
+}
+
+}  // extern "C"

@@ -1,0 +1,76 @@
+// bt709_kernels.cuh — launch-argument structs shared by the kernels (bt709_kernels.cu)
+// and the C ABI (bt709_api.cpp).  Plain PODs, passed by value.
+#pragma once
+#include <cstdint>
+
+#include "bt709_tables.h"
+
+namespace bt709 {
+
+struct DecodeArgs {
+  const uint8_t *y, *c, *a;  // a == nullptr: opaque
+  uint8_t *out;
+  long long py, pc, pa, po;  // row pitches, bytes
+  long long sy, sc, sa, so;  // frame strides, bytes
+  int w, h, nframes;
+  int rows2;            // ceil(h / 2) row pairs per frame
+  int segs;             // 256-pixel segments per row pair (fast kernel)
+  const uint32_t *lut;  // cell LUT of the selected gamma, N + 1 words, device memory
+  float clamp_lo;
+  int cells_log2;
+  MatrixConsts m;
+};
+
+struct RescaleArgs {
+  const uint8_t *in;
+  uint8_t *out;
+  long long pi, po, si, so;
+  int iw, ih, ow, oh, nframes;
+  float scale_x, scale_y;   // (float)iw / (float)ow, (float)ih / (float)oh
+  const float *lin256;      // sRGB byte -> linear float
+  const uint32_t *enc_lut;  // linear float -> sRGB byte (cell LUT)
+  float enc_clamp_lo;
+  int enc_cells_log2;
+};
+
+struct EncodeArgs {
+  const uint8_t *in;
+  uint8_t *y, *c;
+  long long pi, py, pc, si, sy, sc;
+  int w, h, nframes;
+  const float *lin256;     // input-gamma byte -> linear float          (BT709_tolinearNorm)
+  const float *compn256;   // byte -> unorm8(from_linear(to_linear(b)))  (per-pixel luma path)
+  const uint32_t *out_lut;  // linear float -> output-gamma byte (cell LUT, BT709_from_linear)
+  float out_clamp_lo;
+  int out_cells_log2;
+};
+
+struct Packed444Args {
+  const uint32_t *in;
+  uint32_t *out;
+  long long n;           // pixels
+  const float *enc256;   // convert: byte -> apple_oetf(srgb_eotf(b/255))
+  const uint32_t *lut;   // unconvert: Apple decode cell LUT
+  float clamp_lo;
+  int cells_log2;
+  MatrixConsts m;
+};
+
+struct CopyPackedArgs {
+  const uint32_t *in;
+  uint8_t *y, *c;
+  long long py, pc;
+  int w, h;
+};
+
+// launchers (bt709_kernels.cu).  Each returns the cudaError_t of the launch.
+int launch_decode(const DecodeArgs &a, int sm_count, void *stream);
+int launch_rescale(const RescaleArgs &a, int sm_count, void *stream);
+int launch_encode(const EncodeArgs &a, int sm_count, void *stream);
+int launch_convert444(const Packed444Args &a, void *stream);
+int launch_unconvert444(const Packed444Args &a, void *stream);
+int launch_copy_packed(const CopyPackedArgs &a, void *stream);
+// one-time per-device kernel attribute setup (dynamic shared memory opt-in)
+int kernels_init();
+
+}  // namespace bt709

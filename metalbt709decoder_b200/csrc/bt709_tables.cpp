@@ -1,0 +1,205 @@
+// bt709_tables.cpp — see bt709_tables.h.  Host-only; runs once per context.
+#include "bt709_tables.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace bt709 {
+
+static inline uint32_t f2u(float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  return u;
+}
+static inline float u2f(uint32_t u) {
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+
+// ------------------------------------------------------------------ curves
+// Stored values are float32; pow is evaluated in double and the whole right-hand side
+// is rounded to float once, as in the reference headers.
+
+float srgb_eotf(float v) {
+  if (v <= 0.04045f) return v * (1.0f / 12.92f);
+  float s = (v + 0.055f) * (1.0f / (1.0f + 0.055f));
+  return (float) std::pow((double) s, (double) 2.4f);
+}
+
+float srgb_oetf(float v) {
+  if (v <= 0.0031308f) return v * 12.92f;
+  const float a = 0.055f;
+  const float g = 1.0f / 2.4f;
+  return (float) ((double) (1.0f + a) * std::pow((double) v, (double) g) - (double) a);
+}
+
+float bt709_eotf(float v) {
+  if (v < 0.081f) return v * (1.0f / 4.5f);
+  const float a = 0.099f;
+  const float g = 1.0f / 0.45f;
+  float s = (v + a) * (1.0f / (1.0f + a));
+  return (float) std::pow((double) s, (double) g);
+}
+
+static const float kAppleGamma = 1.960938f;
+
+float apple_eotf(float v) {
+  if (v < 0.05583828f) return v * (1.0f / 16.0f);
+  return (float) std::pow((double) v, (double) kAppleGamma);
+}
+
+float apple_oetf(float v) {
+  if (v < 0.00349f) return v * 16.0f;
+  const float g = 1.0f / kAppleGamma;
+  return (float) std::pow((double) v, (double) g);
+}
+
+int quant255(float v) { return (int) std::round((double) (v * 255.0f)); }
+
+int decode_code(int gamma, float x) {
+  switch (gamma) {
+    case kApple: return quant255(srgb_oetf(apple_eotf(x)));
+    case kBt709: return quant255(srgb_oetf(bt709_eotf(x)));
+    case kLinear: return quant255(srgb_oetf(x));
+    default: return quant255(x);
+  }
+}
+
+int from_linear_code(int gamma, float v) {
+  switch (gamma) {
+    case kSrgb: return quant255(srgb_oetf(v));
+    case kApple: return quant255(apple_oetf(v));
+    default: return quant255(v);
+  }
+}
+
+float to_linear(int gamma, int byte) {
+  float n = byte * (1.0f / 255.0f);
+  switch (gamma) {
+    case kSrgb: return srgb_eotf(n);
+    case kApple: return apple_eotf(n);
+    default: return n;
+  }
+}
+
+// ------------------------------------------------------------- step functions
+int StepFn::eval(float x) const {
+  int lo = 0, hi = 255;  // largest k with thr[k] <= x
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (thr[mid] <= x)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  return lo;
+}
+
+bool build_step_fn(CodeFn fn, int mode, StepFn *out) {
+  const uint32_t kOne = 0x3F800000u;  // bits of 1.0f; positive floats order like their bits
+  out->thr[0] = 0.0f;
+  const int top = fn(mode, 1.0f);
+  if (fn(mode, 0.0f) != 0 || top < 0 || top > 255) return false;
+  for (int k = 1; k <= 255; k++) {
+    if (k > top) {
+      out->thr[k] = 2.0f;
+      continue;
+    }
+    uint32_t lo = 0, hi = kOne;  // invariant: code(lo) < k <= code(hi)
+    while (hi - lo > 1) {
+      uint32_t mid = lo + (hi - lo) / 2;
+      if (fn(mode, u2f(mid)) >= k)
+        hi = mid;
+      else
+        lo = mid;
+    }
+    out->thr[k] = u2f(hi);
+    if (k > 1 && !(out->thr[k] >= out->thr[k - 1])) return false;
+  }
+  // verification sample: the counted value must equal the direct evaluation
+  uint32_t s = 0x9E3779B9u;
+  for (int i = 0; i < 200000; i++) {
+    s = s * 1664525u + 1013904223u;
+    float x = u2f((uint32_t) (((uint64_t) s * (kOne + 1ull)) >> 32));
+    if (fn(mode, x) != out->eval(x)) return false;
+  }
+  for (int k = 1; k <= top; k++) {
+    uint32_t b = f2u(out->thr[k]);
+    for (int d = -2; d <= 2; d++) {
+      int64_t bb = (int64_t) b + d;
+      if (bb < 0 || bb > (int64_t) kOne) continue;
+      float x = u2f((uint32_t) bb);
+      if (fn(mode, x) != out->eval(x)) return false;
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------ cell LUT
+// Device lookup (kernels and cell_lut_eval below):
+//     xc   = max(x, clamp_lo)                       clamp_lo = 2^-(n+1)
+//     idx  = trunc(xc * N)                          fma.rz(xc, N, 2^23), low mantissa bits
+//     code = (entries[idx] + bits(xc)) >> 24
+// All floats of one cell share sign and exponent, so bits(xc) = (exp << 23) + mant and
+//     entries[idx] = (base << 24) + (2^24 - field) - (exp << 23)      (mod 2^32)
+// makes the sum (base << 24) + 2^24 - field + mant, whose top byte is base + (mant >= field).
+// field = mantissa of the one threshold inside the cell, or 2^23 (never reached) if none.
+bool build_cell_lut(const StepFn &fn, int cells_log2, CellLut *out) {
+  const int n = cells_log2;
+  const uint32_t N = 1u << n;
+  const float clamp_lo = std::ldexp(1.0f, -(n + 1));
+  if (fn.thr[1] < clamp_lo) return false;  // clamping would change a result
+  out->cells_log2 = n;
+  out->clamp_lo = clamp_lo;
+  out->entries.assign(N + 1, 0u);
+  for (uint32_t i = 0; i <= N; i++) {
+    float lower = (i == 0) ? clamp_lo : (float) i / (float) N;
+    uint32_t lb = f2u(lower);
+    uint32_t base = (uint32_t) fn.eval(lower);
+    uint32_t field = 1u << 23;
+    if (i < N) {
+      float upper = (float) (i + 1) / (float) N;
+      float last = u2f(f2u(upper) - 1);  // largest float below the next cell
+      if ((f2u(last) >> 23) != (lb >> 23)) return false;
+      int cnt = fn.eval(last) - (int) base;
+      if (cnt > 1) return false;
+      if (cnt == 1) field = f2u(fn.thr[base + 1]) & 0x7FFFFFu;
+    }
+    uint32_t exp = lb >> 23;
+    out->entries[i] = (base << 24) + ((1u << 24) - field) - (exp << 23);
+  }
+  return true;
+}
+
+int build_cell_lut_auto(const StepFn &fn, int lo, int hi, CellLut *out) {
+  for (int n = lo; n <= hi; n++)
+    if (build_cell_lut(fn, n, out)) return n;
+  return -1;
+}
+
+int cell_lut_eval(const CellLut &lut, float x) {
+  float xc = x > lut.clamp_lo ? x : lut.clamp_lo;
+  uint32_t idx = (uint32_t) (xc * (float) (1u << lut.cells_log2));  // exact product, truncation
+  return (int) ((lut.entries[idx] + f2u(xc)) >> 24);
+}
+
+// ------------------------------------------------------------------- matrix
+MatrixConsts matrix_consts() {
+  // BT709.h:40-53, 389-397 — float32 arithmetic, left to right
+  const float Kr = 0.2126f, Kg = 0.7152f, Kb = 0.0722f;
+  const float crSpan = 1.5748f, cbSpan = 1.8556f;
+  const float kr_kg = Kr / Kg, kb_kg = Kb / Kg;
+  const float ys = 255.0f / (float) (235 - 16);
+  const float cs = 255.0f / (float) (240 - 16);
+  MatrixConsts m;
+  m.inv255 = 1.0f / 255.0f;
+  m.ys = ys;
+  m.r_cr = cs * crSpan;
+  m.g_cb = -1.0f * cs * cbSpan * kb_kg;
+  m.g_cr = -1.0f * cs * crSpan * kr_kg;
+  m.b_cb = cs * cbSpan;
+  return m;
+}
+
+}  // namespace bt709

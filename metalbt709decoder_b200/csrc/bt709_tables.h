@@ -1,0 +1,71 @@
+// bt709_tables.h — host-side construction of the constant tables a context uploads once.
+//
+// Every transfer-curve evaluation on the device is an exact table lookup:
+//   * an 8-bit input (encode, rescale taps) indexes a 256-entry table;
+//   * a float32 input x in [0,1] (matrix output, 2x2 linear mean, bilinear blend) is
+//     mapped to its 8-bit code by a *step function*  code(x) = #{k : thr[k] <= x},
+//     where thr[k] is the smallest float32 whose reference result is >= k.  The
+//     reference evaluates the curve in double and rounds (BT709.h:711-713), which is a
+//     monotone map float32 -> {0..255}, so 255 thresholds describe it completely and
+//     the device result is bit-identical to the reference for every input.
+//   * the step function is stored as a uniform-cell table ("cell LUT"): the cell index
+//     is trunc(x * N), each cell holds at most one threshold, and one 32-bit entry
+//     encodes {code at the cell start, mantissa of the threshold}; see cell_lut_eval().
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace bt709 {
+
+enum Gamma { kApple = 0, kSrgb = 1, kLinear = 2, kBt709 = 3 };
+
+// ---- scalar curve math with the reference's float32/double semantics ----------------
+float srgb_eotf(float v);   // sRGB.h:43-57
+float srgb_oetf(float v);   // sRGB.h:62-74
+float bt709_eotf(float v);  // BT709.h:68-81
+float apple_eotf(float v);  // BT709.h:125-137
+float apple_oetf(float v);  // BT709.h:139-151
+int quant255(float v);      // BT709.h:711-713
+
+// code(x) of the decode path: matrix output -> sRGB byte, per gamma mode
+int decode_code(int gamma, float x);
+// code(v) of BT709_from_linear (BT709.h:1150-1167): linear float -> output-gamma byte
+int from_linear_code(int gamma, float v);
+// BT709_tolinearNorm (BT709.h:1098-1148) for one byte
+float to_linear(int gamma, int byte);
+
+// ---- step functions ------------------------------------------------------------------
+struct StepFn {
+  // thr[k], k = 1..255: smallest float32 x in [0,1] with code(x) >= k (2.0f if never).
+  // thr[0] = 0.
+  float thr[256];
+  int eval(float x) const;  // reference evaluation by counting (host side, for checks)
+};
+
+typedef int (*CodeFn)(int mode, float x);
+// Bisection over float32 bit patterns; returns false if code() is found non-monotone
+// on the verification sample.
+bool build_step_fn(CodeFn fn, int mode, StepFn *out);
+
+// ---- cell LUT ------------------------------------------------------------------------
+struct CellLut {
+  int cells_log2 = 0;             // N = 1 << cells_log2 uniform cells over [0,1], plus cell N = {1.0}
+  float clamp_lo = 0.f;           // inputs are clamped up to this power of two first (code is 0 below it)
+  std::vector<uint32_t> entries;  // N + 1 words
+};
+// Fails (returns false) if some cell would hold two thresholds or thr[1] < clamp_lo.
+bool build_cell_lut(const StepFn &fn, int cells_log2, CellLut *out);
+// Smallest cells_log2 in [lo, hi] for which build_cell_lut succeeds; -1 if none.
+int build_cell_lut_auto(const StepFn &fn, int lo, int hi, CellLut *out);
+// Host model of the device lookup (bit-for-bit what the kernels do).
+int cell_lut_eval(const CellLut &lut, float x);
+
+// ---- matrix constants, computed in float32 exactly as BT709.h:389-397 ------------------
+struct MatrixConsts {
+  float inv255;  // 1.0f/255.0f
+  float ys;      // 255/219
+  float r_cr, g_cb, g_cr, b_cb;
+};
+MatrixConsts matrix_consts();
+
+}  // namespace bt709

@@ -1,0 +1,169 @@
+"""Parity of the CUDA decode (pass 1) with the CPU oracle, through the C ABI.  -m gpu."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from _oracle import Oracle, frame_lattice, frame_random
+
+pytestmark = pytest.mark.gpu
+ORA = Oracle()
+GAMMAS = [0, 1, 2, 3]
+
+
+def _check(got, want, what):
+    from _gpu import parity_report
+    exact, mx = parity_report(got, want)
+    # north_star gate: +-1 LSB per channel; this implementation is designed to be bit-exact
+    assert mx <= 1, f"{what}: max abs diff {mx} > 1 LSB"
+    assert exact == 1.0, f"{what}: bit-exact fraction {exact:.6f} (max diff {mx})"
+
+
+@pytest.mark.parametrize("gamma", GAMMAS)
+def test_all_2_24_inputs_bit_exact(gamma):
+    """F-lattice: every (Y,Cb,Cr) triple in one 4096x4096 frame."""
+    from _gpu import decode
+    y, c = frame_lattice()
+    _check(decode(gamma, y, c), ORA.decode_nv12(gamma, y, c), f"lattice gamma={gamma}")
+
+
+@pytest.mark.parametrize("gamma", GAMMAS)
+@pytest.mark.parametrize("w,h", [(1920, 1080), (256, 2), (4, 2), (132, 6)])
+def test_random_frames_fast_path(gamma, w, h):
+    from _gpu import decode
+    y, c = frame_random(w, h, seed=709)
+    _check(decode(gamma, y, c), ORA.decode_nv12(gamma, y, c), f"{w}x{h}")
+
+
+@pytest.mark.parametrize("gamma", GAMMAS)
+@pytest.mark.parametrize("w,h", [(37, 21), (1, 1), (2, 2), (3, 5), (130, 7), (258, 3)])
+def test_ragged_sizes_generic_path(gamma, w, h):
+    """odd widths / heights: chroma plane is ceil(w/2) x ceil(h/2) pairs"""
+    from _gpu import decode
+    y, c = frame_random(w, h, seed=710, full_range=True)
+    _check(decode(gamma, y, c), ORA.decode_nv12(gamma, y, c), f"{w}x{h}")
+
+
+def test_full_range_bytes_saturate_like_the_reference():
+    from _gpu import decode
+    y, c = frame_random(512, 64, seed=710, full_range=True)
+    for gamma in GAMMAS:
+        _check(decode(gamma, y, c), ORA.decode_nv12(gamma, y, c), "full range")
+
+
+def test_odd_height_on_fast_path():
+    from _gpu import decode
+    y, c = frame_random(256, 5, seed=3)
+    _check(decode(0, y, c), ORA.decode_nv12(0, y, c), "256x5")
+
+
+def test_padded_pitches_and_unaligned_bases():
+    """planes with row padding (CoreVideo bytesPerRow) and a base pointer that is not 4-aligned"""
+    from _gpu import ctx, dev
+    w, h = 200, 10
+    y, c = frame_random(w, h, seed=11)
+    want = ORA.decode_nv12(3, y, c)
+    yp = np.zeros((h, 256), np.uint8); yp[:, :w] = y
+    cp = np.zeros((h // 2, 320), np.uint8); cp[:, :w] = c
+    ty, tc = dev(yp)[None], dev(cp)[None]
+    out = torch.zeros((1, h, 208, 4), dtype=torch.uint8, device="cuda")
+    ctx().decode_nv12(3, ty, tc, out, w=w, h=h, wait=True)
+    _check(out[0, :, :w].cpu().numpy(), want, "padded")
+    assert int(out[0, :, w:].max()) == 0  # padding untouched
+    # unaligned base: shift the Y plane by one byte inside a larger allocation
+    flat = torch.zeros(h * 256 + 1, dtype=torch.uint8, device="cuda")
+    flat[1:] = ty.reshape(-1)
+    ty2 = flat[1:].view(1, h, 256)
+    out.zero_()
+    ctx().decode_nv12(3, ty2, tc, out, w=w, h=h, wait=True)
+    _check(out[0, :, :w].cpu().numpy(), want, "unaligned")
+
+
+def test_batch_of_frames_matches_per_frame():
+    from _gpu import ctx, dev
+    w, h, F = 640, 360, 5
+    ys, cs, wants = [], [], []
+    for f in range(F):
+        y, c = frame_random(w, h, seed=709 + f)
+        ys.append(y); cs.append(c); wants.append(ORA.decode_nv12(0, y, c))
+    ty, tc = dev(np.stack(ys)), dev(np.stack(cs))
+    out = torch.zeros((F, h, w, 4), dtype=torch.uint8, device="cuda")
+    ctx().decode_nv12(0, ty, tc, out, wait=True)
+    _check(out.cpu().numpy(), np.stack(wants), "batch")
+
+
+@pytest.mark.parametrize("w,h", [(2048, 16), (50, 9)])
+def test_alpha_stream(w, h):
+    """C4: RGB stream + alpha stream's Y plane -> BGRA with A, sRGB gamma, no premultiply"""
+    from _gpu import decode
+    y, c = frame_random(w, h, seed=21)
+    a, _ = frame_random(w, h, seed=22, full_range=True)
+    got = decode(1, y, c, alpha=a)
+    want = ORA.decode_nv12(1, y, c, alpha_y=a)
+    _check(got, want, "alpha")
+    assert set(np.unique(want[..., 3])) != {255}
+
+
+def test_error_codes():
+    from _gpu import ctx, dev
+    from metalbt709decoder_b200 import BT709Error
+    from metalbt709decoder_b200._lib import Plane
+    C = ctx()
+    y, c = frame_random(16, 8)
+    ty, tc = dev(y)[None], dev(c)[None]
+    out = torch.zeros((1, 8, 16, 4), dtype=torch.uint8, device="cuda")
+    with pytest.raises(BT709Error) as e:
+        C.decode_nv12(7, ty, tc, out)
+    assert e.value.status == -4  # BT709_E_GAMMA
+    with pytest.raises(BT709Error) as e:
+        C.decode_nv12(0, ty, tc, out, alpha_y=ty)
+    assert e.value.status == -5  # alpha needs sRGB (MetalBT709Decoder.m:165-169)
+    with pytest.raises(BT709Error) as e:
+        C.decode_nv12(0, ty, tc, out, w=0)
+    assert e.value.status == -2
+    with pytest.raises(BT709Error) as e:
+        C.decode_nv12(0, ty, tc, out, w=32)  # pitch (16) < row bytes (32)
+    assert e.value.status == -3
+    p = Plane(None, 16, 0)
+    assert C.decode_nv12_raw(0, ctypes.byref(p), ctypes.byref(p), None, ctypes.byref(p), 16, 8, 1) == -1
+    assert C.last_cuda_error() == 0
+
+
+def test_async_then_stream_sync_and_launch_count():
+    from _gpu import ctx, dev
+    C = ctx()
+    y, c = frame_random(1920, 1080, seed=1)
+    ty, tc = dev(y)[None], dev(c)[None]
+    out = torch.zeros((1, 1080, 1920, 4), dtype=torch.uint8, device="cuda")
+    s = torch.cuda.Stream()
+    n0 = C.launch_count
+    with torch.cuda.stream(s):
+        C.decode_nv12(3, ty, tc, out, stream=s, wait=False)
+    s.synchronize()
+    assert C.launch_count == n0 + 1
+    _check(out[0].cpu().numpy(), ORA.decode_nv12(3, y, c), "async")
+
+
+def test_uhd_frame_size_independent_properties():
+    """BASELINE config sizes: properties that do not need the oracle at full size.
+    (1) decode is a per-pixel map: shuffling 2x2 blocks commutes with decoding;
+    (2) neutral chroma gives R=G=B; (3) a spot-checked band matches the oracle."""
+    from _gpu import decode
+    w, h = 3840, 2160
+    y, c = frame_random(w, h, seed=4)
+    got = decode(0, y, c)
+    band = slice(1000, 1016)
+    _check(got[band], ORA.decode_nv12(0, y[band], c[500:508]), "UHD band")
+    yb = y.reshape(h // 2, 2, w // 2, 2)
+    cb = c.reshape(h // 2, w // 2, 2)
+    perm = np.random.default_rng(0).permutation(w // 2)
+    y2 = yb[:, :, perm, :].reshape(h, w)
+    c2 = cb[:, perm, :].reshape(h // 2, w)
+    got2 = decode(0, y2, c2)
+    ref2 = got.reshape(h // 2, 2, w // 2, 2, 4)[:, :, perm].reshape(h, w, 4)
+    assert np.array_equal(got2, ref2)
+    cn = np.full_like(c, 128)
+    g = decode(3, y, cn)
+    assert np.array_equal(g[..., 0], g[..., 1]) and np.array_equal(g[..., 1], g[..., 2])
+    assert (g[..., 3] == 255).all()
