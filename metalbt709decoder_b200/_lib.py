@@ -9,7 +9,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbt709_b200.so")
+LIB_PATH = os.environ.get("BT709_B200_LIB") or os.path.join(_HERE, "libbt709_b200.so")  # env: kernel experiments only
 CSRC = os.path.join(_HERE, "csrc")
 
 c_void_p, c_int, c_size_t, c_u32p = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(ctypes.c_uint32)
@@ -113,7 +113,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if _needs_build():
+    if "BT709_B200_LIB" not in os.environ and _needs_build():
         build()
     L = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():

@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <cstdlib>
 
 #include "bt709_kernels.cuh"
 
@@ -53,6 +54,14 @@ __device__ __forceinline__ void st_stream_u32(void *p, uint32_t v) {
   asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// base + a * b with 32-bit unsigned a, b: one IMAD.WIDE.U32 (the compiler's own 64-bit address
+// arithmetic spent ~7 instructions per pixel on sign extensions and carry chains)
+__device__ __forceinline__ const uint8_t *ptr_mad(const uint8_t *base, unsigned a, unsigned b) {
+  unsigned long long r;
+  asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"((unsigned long long) base));
+  return (const uint8_t *) r;
+}
+
 // round-half-away-from-zero of a non-negative float, exactly: the +0.5 is done with
 // round-toward-zero so it can never be rounded up across an integer.
 __device__ __forceinline__ int round_pos(float r) {
@@ -84,132 +93,403 @@ __device__ __forceinline__ uint32_t lut_code(const uint32_t *lut, float x, float
 }
 
 // ============================================================================ decode, fast
-// One warp owns a segment of 256 pixels x 2 rows (one chroma row).  Lane l handles pixels
-// [4l, 4l+4) and [128+4l, 128+4l+4) of both rows, so every warp-level access is contiguous:
-//   Y     2 rows x 2 x LDG.32   (128 B per instruction)
-//   CbCr  2 x LDG.32            (128 B per instruction; loaded once, used for both rows)
-//   BGRA  2 rows x 2 x STG.128  (512 B per instruction)
+// One warp owns a strip of consecutive 128-pixel x 2-row segments (one chroma row).  In a
+// segment lane l handles pixels [4l, 4l+4) of both rows, so every warp-level access is contiguous:
+//   Y     2 rows x LDG.32   (128 B per instruction)
+//   CbCr  1 x LDG.32        (128 B per instruction; loaded once, used for both rows)
+//   BGRA  2 rows x STG.128  (512 B per instruction)
+// The next segment's loads are issued before the current one is computed (software prefetch).
 // Grid: persistent, one CTA per SM (the replicated LUT takes 128 KB of shared memory).
-template <int CL2, int RL2, bool ALPHA>
-__device__ __forceinline__ void decode_quad(uint32_t yw0, uint32_t yw1, uint32_t cw, uint32_t aw0, uint32_t aw1,
-                                            const MatrixConsts &m, float clamp_lo, uint32_t sbase, uint4 &o0,
-                                            uint4 &o1) {
-  const float kY = 8388608.0f + 16.0f, kC = 8388608.0f + 128.0f;
-  uint32_t r0[4], r1[4];
-#pragma unroll
-  for (int pr = 0; pr < 2; pr++) {
-    // chroma pair pr: bytes 2pr (Cb), 2pr+1 (Cr).  BT709.h:499-500 then the matrix columns.
-    float cbn = __fmul_rn(pr == 0 ? byte_minus<0>(cw, kC) : byte_minus<2>(cw, kC), m.inv255);
-    float crn = __fmul_rn(pr == 0 ? byte_minus<1>(cw, kC) : byte_minus<3>(cw, kC), m.inv255);
-    float cb_g = __fmul_rn(cbn, m.g_cb), cb_b = __fmul_rn(cbn, m.b_cb);
-    float cr_r = __fmul_rn(crn, m.r_cr), cr_g = __fmul_rn(crn, m.g_cr);
-#pragma unroll
-    for (int row = 0; row < 2; row++) {
-      uint32_t yw = row ? yw1 : yw0;
-      uint32_t aw = row ? aw1 : aw0;
-#pragma unroll
-      for (int px = 0; px < 2; px++) {
-        const int k = pr * 2 + px;
-        float yf = k == 0 ? byte_minus<0>(yw, kY) : k == 1 ? byte_minus<1>(yw, kY)
-                 : k == 2 ? byte_minus<2>(yw, kY) : byte_minus<3>(yw, kY);
-        float yt = __fmul_rn(__fmul_rn(yf, m.inv255), m.ys);            // BT709.h:494, 424
-        float xr = add_sat(yt, cr_r);                                   // + Cb*0 is a no-op
-        float xg = add_sat(__fadd_rn(yt, cb_g), cr_g);                  // (Y + Cb) + Cr order
-        float xb = add_sat(yt, cb_b);
-        uint32_t sr = lut_sum_smem<CL2, RL2>(xr, clamp_lo, sbase);
-        uint32_t sg = lut_sum_smem<CL2, RL2>(xg, clamp_lo, sbase);
-        uint32_t sb = lut_sum_smem<CL2, RL2>(xb, clamp_lo, sbase);
-        uint32_t bg = __byte_perm(sb, sg, 0x0073);  // byte0 = B code, byte1 = G code
-        uint32_t w;
-        if (ALPHA) {
-          // AAPLShaders.metal:249-271 via the CPU twin BT709.h:466-513 with neutral chroma
-          float af = k == 0 ? byte_minus<0>(aw, kY) : k == 1 ? byte_minus<1>(aw, kY)
-                   : k == 2 ? byte_minus<2>(aw, kY) : byte_minus<3>(aw, kY);
-          float an = add_sat(__fmul_rn(__fmul_rn(af, m.inv255), m.ys), 0.0f);
-          uint32_t ac = (uint32_t) round_pos(__fmul_rn(an, 255.0f));
-          uint32_t ra = __byte_perm(sr, ac, 0x0043);  // byte0 = R code, byte1 = alpha
-          w = __byte_perm(bg, ra, 0x5410);
-        } else {
-          w = __byte_perm(bg, sr, 0x7710) | 0xFF000000u;  // A = 255 (AAPLShaders.metal:243)
-        }
-        if (row) r1[k] = w; else r0[k] = w;
-      }
-    }
-  }
-  o0 = make_uint4(r0[0], r0[1], r0[2], r0[3]);
-  o1 = make_uint4(r1[0], r1[1], r1[2], r1[3]);
+//
+// The float32 steps of the matrix are done two pixels at a time with the Blackwell packed
+// instructions (add/mul/fma .f32x2 -> FADD2/FMUL2/FFMA2): identical IEEE results per lane, half
+// the issue slots.  A pair always holds the same pixel position of chroma pair A (pixels 0,1) and
+// chroma pair B (pixels 2,3), so chroma products pair up naturally with the luma terms.
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f32x2 pku(uint32_t lo, uint32_t hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ void upku(f32x2 v, uint32_t &lo, uint32_t &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2_rz(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rz.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
 }
 
-template <int CL2, int RL2, bool ALPHA, int THREADS>
+// loop-invariant packed constants {k, k}
+struct DecodeK2 {
+  f32x2 kY, kC, inv255, ys, g_cb, b_cb, r_cr, g_cr, fN, magic;
+};
+
+template <int K>
+__device__ __forceinline__ uint32_t magic_byte(uint32_t word) {  // bits of the float 2^23 + byte K
+  return __byte_perm(word, 0x4B000000u, 0x7540 + K);
+}
+
+// two LUT lookups at once: clamp (scalar), index (packed FFMA2.RZ), two LDS, two adds.
+// returns the two sums whose byte 3 is the 8-bit code
+template <int CL2, int RL2>
+__device__ __forceinline__ void lut2(float xa, float xb, float clamp_lo, const DecodeK2 &k, uint32_t sbase,
+                                     uint32_t &sa, uint32_t &sb) {
+  float ca = fmaxf(xa, clamp_lo), cb = fmaxf(xb, clamp_lo);
+  uint32_t ta, tb;
+  upku(fma2_rz(pk(ca, cb), k.fN, k.magic), ta, tb);
+  uint32_t ea, eb;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(ea) : "r"((ta << (2 + RL2)) + sbase));
+  asm("ld.shared.u32 %0, [%1];" : "=r"(eb) : "r"((tb << (2 + RL2)) + sbase));
+  sa = ea + __float_as_uint(ca);
+  sb = eb + __float_as_uint(cb);
+}
+
+template <int CL2, int RL2, bool ALPHA>
+__device__ __forceinline__ uint4 decode_row(uint32_t yw, uint32_t aw, f32x2 cb_g, f32x2 cb_b, f32x2 cr_r, f32x2 cr_g,
+                                            const DecodeK2 &k, float clamp_lo, uint32_t sbase) {
+  // luma terms, BT709.h:494 then :424 — pairs (px0, px2) and (px1, px3)
+  f32x2 y02 = mul2(mul2(add2(pku(magic_byte<0>(yw), magic_byte<2>(yw)), k.kY), k.inv255), k.ys);
+  f32x2 y13 = mul2(mul2(add2(pku(magic_byte<1>(yw), magic_byte<3>(yw)), k.kY), k.inv255), k.ys);
+  float y0, y1, y2, y3, crA, crB, cgA, cgB, cbA, cbB, bgA, bgB;
+  upk(y02, y0, y2); upk(y13, y1, y3);
+  upk(cr_r, crA, crB); upk(cr_g, cgA, cgB); upk(cb_b, cbA, cbB); upk(cb_g, bgA, bgB);
+  // (Y + Cb) first, then + Cr (BT709.h:425).  Scalar adds on purpose: ptxas contracts a packed
+  // mul.rn.f32x2 feeding an add.rn.f32x2 into FFMA2 (one rounding instead of two), which would
+  // break bit-exactness; it never contracts a packed multiply with a scalar add.rn.
+  const float g0 = __fadd_rn(y0, bgA), g1 = __fadd_rn(y1, bgA), g2 = __fadd_rn(y2, bgB), g3 = __fadd_rn(y3, bgB);
+  uint32_t r0, r1, r2, r3, gg0, gg1, gg2, gg3, b0, b1, b2, b3;
+  lut2<CL2, RL2>(add_sat(y0, crA), add_sat(y2, crB), clamp_lo, k, sbase, r0, r2);
+  lut2<CL2, RL2>(add_sat(y1, crA), add_sat(y3, crB), clamp_lo, k, sbase, r1, r3);
+  lut2<CL2, RL2>(add_sat(g0, cgA), add_sat(g2, cgB), clamp_lo, k, sbase, gg0, gg2);
+  lut2<CL2, RL2>(add_sat(g1, cgA), add_sat(g3, cgB), clamp_lo, k, sbase, gg1, gg3);
+  lut2<CL2, RL2>(add_sat(y0, cbA), add_sat(y2, cbB), clamp_lo, k, sbase, b0, b2);
+  lut2<CL2, RL2>(add_sat(y1, cbA), add_sat(y3, cbB), clamp_lo, k, sbase, b1, b3);
+  uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (ALPHA) {
+    // AAPLShaders.metal:249-271 via the CPU twin BT709.h:466-513 with neutral chroma
+    f32x2 a02 = mul2(mul2(add2(pku(magic_byte<0>(aw), magic_byte<2>(aw)), k.kY), k.inv255), k.ys);
+    f32x2 a13 = mul2(mul2(add2(pku(magic_byte<1>(aw), magic_byte<3>(aw)), k.kY), k.inv255), k.ys);
+    float f0, f1, f2, f3;
+    upk(a02, f0, f2); upk(a13, f1, f3);
+    a0 = (uint32_t) round_pos(__fmul_rn(add_sat(f0, 0.0f), 255.0f));
+    a1 = (uint32_t) round_pos(__fmul_rn(add_sat(f1, 0.0f), 255.0f));
+    a2 = (uint32_t) round_pos(__fmul_rn(add_sat(f2, 0.0f), 255.0f));
+    a3 = (uint32_t) round_pos(__fmul_rn(add_sat(f3, 0.0f), 255.0f));
+  }
+  auto pack = [](uint32_t sb, uint32_t sg, uint32_t sr, uint32_t a) -> uint32_t {
+    uint32_t bg = __byte_perm(sb, sg, 0x0073);  // byte0 = B code, byte1 = G code
+    if (ALPHA) return __byte_perm(bg, __byte_perm(sr, a, 0x0043), 0x5410);
+    return __byte_perm(bg, sr, 0x7710) | 0xFF000000u;  // A = 255 (AAPLShaders.metal:243)
+  };
+  return make_uint4(pack(b0, gg0, r0, a0), pack(b1, gg1, r1, a1), pack(b2, gg2, r2, a2), pack(b3, gg3, r3, a3));
+}
+
+// Work layout.  A warp owns a 128-pixel x 2-row tile (lane l: pixels [4l, 4l+4) of both rows).
+// The warps of the CTA sit side by side: they cover `rps` complete row pairs per step
+// (rps = warps / tiles per row), so a CTA touches 2*rps whole contiguous rows of Y, rps rows of
+// CbCr and 2*rps rows of BGRA at a time, and consecutive CTAs take consecutive bands.  That keeps
+// DRAM pages hot (a warp streaming its own row did not: 4736 independent row streams measured
+// 51 % long-scoreboard stalls at 4.2 TB/s).  Each warp's (tile, row-in-band) is fixed for the whole
+// kernel; per step only (frame, row pair) advance, by a constant with a carry, and every address
+// is two IMAD.WIDE away.  The loads of the next step are issued before the current step is
+// computed; the loop is unrolled twice so the two load buffers ping-pong without moves.
+// FULL = (w % 128 == 0 && h % 2 == 0): no per-lane or per-row predicates anywhere.
+template <bool ALPHA>
+struct TileLoad {
+  uint32_t y0, y1, c, a0, a1;
+};
+
+// Addressing.  Every plane is addressed as base + 32-bit offset in load/store units (4 bytes
+// for Y / CbCr / alpha, 16 bytes for BGRA), so an address is a single IMAD.WIDE.U32 and stepping
+// to the next (frame, row pair) is one 32-bit add per plane plus a predicated add on a frame
+// wrap.  The launcher splits batches whose offsets would not fit in 32 bits.
+template <bool ALPHA, bool FULL>
+__device__ __forceinline__ void tile_load(const DecodeArgs &p, unsigned oy, unsigned oc, unsigned oa, unsigned rp,
+                                          bool valid, TileLoad<ALPHA> &t) {
+  const bool has_row1 = FULL || rp * 2 + 1 < (unsigned) p.h;
+  if (!FULL) t.y0 = t.y1 = t.c = t.a0 = t.a1 = 0;
+  if (FULL || valid) {
+    t.y0 = ld_stream_u32(ptr_mad(p.y, oy, 4));
+    t.c = ld_stream_u32(ptr_mad(p.c, oc, 4));
+    if (has_row1) t.y1 = ld_stream_u32(ptr_mad(p.y, oy + p.py4, 4));
+    if (ALPHA) {
+      t.a0 = ld_stream_u32(ptr_mad(p.a, oa, 4));
+      if (has_row1) t.a1 = ld_stream_u32(ptr_mad(p.a, oa + p.pa4, 4));
+    }
+  }
+}
+
+template <int CL2, int RL2, bool ALPHA, bool FULL>
+__device__ __forceinline__ void tile_compute_store(const DecodeArgs &p, unsigned oo, unsigned rp, bool valid,
+                                                   const TileLoad<ALPHA> &t, const DecodeK2 &k, float clamp_lo,
+                                                   uint32_t sbase) {
+  if (!FULL && !valid) return;
+  const bool has_row1 = FULL || rp * 2 + 1 < (unsigned) p.h;
+  // chroma pairs A (bytes 0,1) and B (bytes 2,3): BT709.h:499-500 then the matrix columns
+  f32x2 cbn = mul2(add2(pku(magic_byte<0>(t.c), magic_byte<2>(t.c)), k.kC), k.inv255);
+  f32x2 crn = mul2(add2(pku(magic_byte<1>(t.c), magic_byte<3>(t.c)), k.kC), k.inv255);
+  f32x2 cb_g = mul2(cbn, k.g_cb), cb_b = mul2(cbn, k.b_cb);
+  f32x2 cr_r = mul2(crn, k.r_cr), cr_g = mul2(crn, k.g_cr);
+  st_stream_u128((uint8_t *) ptr_mad(p.out, oo, 16),
+                 decode_row<CL2, RL2, ALPHA>(t.y0, t.a0, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+  if (has_row1)
+    st_stream_u128((uint8_t *) ptr_mad(p.out, oo + p.po16, 16),
+                   decode_row<CL2, RL2, ALPHA>(t.y1, t.a1, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+}
+
+template <int CL2, int RL2, bool ALPHA, bool FULL, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) {
-  extern __shared__ __align__(16) uint32_t s_lut[];
+  extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = 1 << CL2, R = 1 << RL2;
   for (int i = threadIdx.x; i < (N + 1) * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
   const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(s_lut) + ((lane & (R - 1)) << 2) -
                          (0x4B000000u << (2 + RL2));
-  constexpr int WPC = THREADS / 32;
-  const unsigned nwarps = gridDim.x * WPC;
-  const unsigned total = (unsigned) p.nframes * p.rows2 * p.segs;
-  unsigned unit = blockIdx.x * WPC + (threadIdx.x >> 5);
-  if (unit >= total) return;
-  // unit -> (frame, row pair, segment), then stepped incrementally (no division in the loop)
-  unsigned seg = unit % p.segs, rpg = unit / p.segs;
-  unsigned rp = rpg % p.rows2, f = rpg / p.rows2;
-  const unsigned d_seg = nwarps % p.segs, d_rpg = nwarps / p.segs;
-  const unsigned d_rp = d_rpg % p.rows2, d_f = d_rpg / p.rows2;
-  const MatrixConsts m = p.m;
   const float clamp_lo = p.clamp_lo;
+  DecodeK2 k;
+  k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
+  k.kC = pk(-(8388608.0f + 128.0f), -(8388608.0f + 128.0f));
+  k.inv255 = pk(p.m.inv255, p.m.inv255);
+  k.ys = pk(p.m.ys, p.m.ys);
+  k.g_cb = pk(p.m.g_cb, p.m.g_cb);
+  k.b_cb = pk(p.m.b_cb, p.m.b_cb);
+  k.r_cr = pk(p.m.r_cr, p.m.r_cr);
+  k.g_cr = pk(p.m.g_cr, p.m.g_cr);
+  k.fN = pk((float) N, (float) N);
+  k.magic = pk(8388608.0f, 8388608.0f);
 
-  for (; unit < total; unit += nwarps) {
-    const int col0 = seg * 256 + lane * 4;
-    const int row0 = rp * 2;
-    const bool has_row1 = row0 + 1 < p.h;
-    const uint8_t *yp = p.y + f * p.sy + (long long) row0 * p.py + col0;
-    const uint8_t *cp = p.c + f * p.sc + (long long) rp * p.pc + col0;
-    uint8_t *op = p.out + f * p.so + (long long) row0 * p.po + (long long) col0 * 4;
-    const uint8_t *ap = ALPHA ? p.a + f * p.sa + (long long) row0 * p.pa + col0 : nullptr;
-    const bool v0 = col0 < p.w, v1 = col0 + 128 < p.w;
+  // this warp's place in the CTA's band: fixed for the whole kernel
+  const unsigned r_local = warp / p.tiles_per_row;
+  if (r_local >= (unsigned) p.rps) return;  // spare warps when the warp count is not a multiple of the tiles per row
+  const unsigned tile0 = warp - r_local * p.tiles_per_row;
+  const unsigned rows2 = p.rows2;
+  const unsigned total_rp = (unsigned) p.nframes * rows2;
+  const unsigned rpg0 = blockIdx.x * p.rps + r_local;
+  if (rpg0 >= total_rp) return;
+  const unsigned f0 = rpg0 / rows2, rp0 = rpg0 - f0 * rows2;
+  const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;  // >= 1
 
-    uint32_t y00 = 0, y01 = 0, y10 = 0, y11 = 0, c0 = 0, c1 = 0, a00 = 0, a01 = 0, a10 = 0, a11 = 0;
-    if (v0) {
-      y00 = ld_stream_u32(yp);
-      c0 = ld_stream_u32(cp);
-      if (has_row1) y10 = ld_stream_u32(yp + p.py);
-      if (ALPHA) {
-        a00 = ld_stream_u32(ap);
-        if (has_row1) a10 = ld_stream_u32(ap + p.pa);
-      }
+  for (unsigned tile = tile0; tile < (unsigned) p.tiles_per_row; tile += p.tile_stride) {
+    const unsigned col4 = tile * 32 + lane;  // column in 4-pixel units
+    const bool valid = FULL || (int) (col4 * 4) < p.w;
+    // load offsets (run one step ahead) and store offset
+    unsigned oy = f0 * p.sy4 + rp0 * 2 * p.py4 + col4;
+    unsigned oc = f0 * p.sc4 + rp0 * p.pc4 + col4;
+    unsigned oa = ALPHA ? f0 * p.sa4 + rp0 * 2 * p.pa4 + col4 : 0;
+    unsigned oo = f0 * p.so16 + rp0 * 2 * p.po16 + col4;
+    unsigned rp = rp0;  // row pair of the data in A at the top of the loop
+    unsigned left = nsteps;
+    TileLoad<ALPHA> A, B;
+    tile_load<ALPHA, FULL>(p, oy, oc, oa, rp, valid, A);
+    while (true) {
+      // ---- A holds step k; prefetch step k+1 into B
+      unsigned rpn = rp + p.d_rp;
+      const bool wrap_a = rpn >= rows2;
+      oy += p.dy; oc += p.dc;
+      if (ALPHA) oa += p.da;
+      if (wrap_a) { rpn -= rows2; oy += p.wy; oc += p.wc; if (ALPHA) oa += p.wa; }
+      if (left > 1) tile_load<ALPHA, FULL>(p, oy, oc, oa, rpn, valid, B);
+      tile_compute_store<CL2, RL2, ALPHA, FULL>(p, oo, rp, valid, A, k, clamp_lo, sbase);
+      if (left == 1) break;
+      oo += p.dout;
+      if (wrap_a) oo += p.wout;
+      // ---- B holds step k+1; prefetch step k+2 into A
+      rp = rpn + p.d_rp;
+      const bool wrap_b = rp >= rows2;
+      oy += p.dy; oc += p.dc;
+      if (ALPHA) oa += p.da;
+      if (wrap_b) { rp -= rows2; oy += p.wy; oc += p.wc; if (ALPHA) oa += p.wa; }
+      if (left > 2) tile_load<ALPHA, FULL>(p, oy, oc, oa, rp, valid, A);
+      tile_compute_store<CL2, RL2, ALPHA, FULL>(p, oo, rpn, valid, B, k, clamp_lo, sbase);
+      if (left == 2) break;
+      oo += p.dout;
+      if (wrap_b) oo += p.wout;
+      left -= 2;
     }
-    if (v1) {
-      y01 = ld_stream_u32(yp + 128);
-      c1 = ld_stream_u32(cp + 128);
-      if (has_row1) y11 = ld_stream_u32(yp + p.py + 128);
-      if (ALPHA) {
-        a01 = ld_stream_u32(ap + 128);
-        if (has_row1) a11 = ld_stream_u32(ap + p.pa + 128);
-      }
-    }
-    if (v0) {
-      uint4 o0, o1;
-      decode_quad<CL2, RL2, ALPHA>(y00, y10, c0, a00, a10, m, clamp_lo, sbase, o0, o1);
-      st_stream_u128(op, o0);
-      if (has_row1) st_stream_u128(op + p.po, o1);
-    }
-    if (v1) {
-      uint4 o0, o1;
-      decode_quad<CL2, RL2, ALPHA>(y01, y11, c1, a01, a11, m, clamp_lo, sbase, o0, o1);
-      st_stream_u128(op + 512, o0);
-      if (has_row1) st_stream_u128(op + p.po + 512, o1);
-    }
+  }
+}
 
-    seg += d_seg;
-    rp += d_rp;
-    f += d_f;
-    if (seg >= (unsigned) p.segs) { seg -= p.segs; rp++; }
-    if (rp >= (unsigned) p.rows2) { rp -= p.rows2; f++; }
+// ===================================================================== decode, bulk-staged
+// Same arithmetic and the same CTA-band work layout as k_decode_fast, but the input planes reach
+// the SM through the bulk async-copy engine (cp.async.bulk -> UBLKCP, the 1-D TMA path) into a
+// shared-memory ring instead of through per-thread LDG into registers.
+//
+// Why: with per-thread loads the bytes in flight per SM are bounded by registers
+// (32 warps x 3 x 128 B = 12 KB), and the measured throughput was the same 4.46 TB/s with the
+// arithmetic compiled out - a latency (Little's law) bound, not an issue bound.  A ring of up to 8
+// stages x 11.5 KB keeps ~90 KB of reads in flight per SM, costs no registers, and removes every
+// load address computation from the consumer warps.
+//
+//   stage  = one CTA band: 2*rps rows of Y and rps rows of CbCr (and 2*rps rows of alpha),
+//            each row one bulk copy of w bytes, issued by lane 0 of warp j for row j
+//   full[s]   mbarrier, count = rows per stage, completes when all bytes of the stage have landed
+//   empty[s]  mbarrier, count = consumer warps, completes when every warp has read its words
+// Requires w % 128 == 0, h even, 16-byte aligned planes and pitches (else k_decode_fast).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+template <int CL2, int RL2, bool ALPHA, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_decode_bulk(const DecodeArgs p) {
+  extern __shared__ __align__(128) uint32_t s_lut[];
+  constexpr int N = 1 << CL2, R = 1 << RL2;
+  constexpr uint32_t kLutBytes = (uint32_t) (N + 1) * R * 4;
+  for (int i = threadIdx.x; i < (N + 1) * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+
+  const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_lut);
+  const uint32_t ring0 = smem0 + kLutBytes;
+  const uint32_t S = p.nstages;
+  const uint32_t bar_full = ring0 + S * p.stage_bytes, bar_empty = bar_full + 8 * S;
+  const unsigned nwarps_active = p.rps * p.tiles_per_row;
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < S; i++) {
+      mbar_init(bar_full + 8 * i, p.nrows);
+      mbar_init(bar_empty + 8 * i, nwarps_active);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - (0x4B000000u << (2 + RL2));
+  const float clamp_lo = p.clamp_lo;
+  DecodeK2 k;
+  k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
+  k.kC = pk(-(8388608.0f + 128.0f), -(8388608.0f + 128.0f));
+  k.inv255 = pk(p.m.inv255, p.m.inv255);
+  k.ys = pk(p.m.ys, p.m.ys);
+  k.g_cb = pk(p.m.g_cb, p.m.g_cb);
+  k.b_cb = pk(p.m.b_cb, p.m.b_cb);
+  k.r_cr = pk(p.m.r_cr, p.m.r_cr);
+  k.g_cr = pk(p.m.g_cr, p.m.g_cr);
+  k.fN = pk((float) N, (float) N);
+  k.magic = pk(8388608.0f, 8388608.0f);
+
+  if (warp >= nwarps_active) return;  // spare warps
+  const unsigned rows2 = p.rows2, rps = p.rps, w = p.w;
+  const unsigned total_rp = (unsigned) p.nframes * rows2;
+  const unsigned nbands = (total_rp + rps - 1) / rps;
+  if (blockIdx.x >= nbands) return;
+  const unsigned nsteps = (nbands - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const unsigned r_local = warp / p.tiles_per_row;
+  const unsigned tile = warp - r_local * p.tiles_per_row;
+
+  // ---- producer role: lane 0 of warp j feeds row j of every stage
+  const bool producer = lane == 0 && warp < (unsigned) p.nrows;
+  unsigned prow_rr = 0, prow_dst = 0;          // row pair within the band; byte offset within a stage
+  const uint8_t *pbase = nullptr;              // plane base
+  unsigned pstride = 0, ppitch = 0, prow_mul = 0, prow_add = 0;  // frame stride; pitch; row = rp*mul + add
+  if (producer) {
+    const unsigned j = warp;
+    if (j < 2 * rps) {
+      prow_rr = j >> 1; pbase = p.y; pstride = (unsigned) p.sy; ppitch = (unsigned) p.py; prow_mul = 2; prow_add = j & 1;
+    } else if (j < 3 * rps) {
+      prow_rr = j - 2 * rps; pbase = p.c; pstride = (unsigned) p.sc; ppitch = (unsigned) p.pc; prow_mul = 1; prow_add = 0;
+    } else {
+      const unsigned q = j - 3 * rps;
+      prow_rr = q >> 1; pbase = p.a; pstride = (unsigned) p.sa; ppitch = (unsigned) p.pa; prow_mul = 2; prow_add = q & 1;
+    }
+    prow_dst = j * w;
+  }
+  auto produce = [&](unsigned kp) {
+    if (!producer || kp >= nsteps) return;
+    const uint32_t slot = kp % S;
+    if (kp >= S) mbar_wait(bar_empty + 8 * slot, ((kp / S) - 1) & 1);
+    const unsigned rpg = (blockIdx.x + kp * gridDim.x) * rps + prow_rr;
+    const uint32_t bar = bar_full + 8 * slot;
+    if (rpg < total_rp) {
+      const unsigned f = rpg / rows2, rp = rpg - f * rows2;
+      const uint8_t *src = ptr_mad(ptr_mad(pbase, f, pstride), rp * prow_mul + prow_add, ppitch);
+      mbar_expect_tx(bar, w);
+      bulk_g2s(ring0 + slot * p.stage_bytes + prow_dst, src, w, bar);
+    } else {
+      mbar_arrive(bar);  // band runs past the last row pair: nothing to copy for this row
+    }
+  };
+
+  // ---- consumer role
+  const unsigned col4 = tile * 32 + lane;
+  const uint32_t my_y = 2 * r_local * w + col4 * 4;              // byte offsets within a stage
+  const uint32_t my_c = (2 * rps + r_local) * w + col4 * 4;
+  const uint32_t my_a = (3 * rps + 2 * r_local) * w + col4 * 4;
+  unsigned rpg = blockIdx.x * rps + r_local;
+  unsigned f0 = rpg / rows2, rp = rpg - f0 * rows2;
+  unsigned oo = f0 * p.so16 + rp * 2 * p.po16 + col4;
+
+  for (unsigned kp = 0; kp + 1 < S; kp++) produce(kp);
+  for (unsigned kk = 0; kk < nsteps; kk++) {
+    produce(kk + S - 1);
+    const uint32_t slot = kk % S;
+    mbar_wait(bar_full + 8 * slot, (kk / S) & 1);
+    const uint32_t st = ring0 + slot * p.stage_bytes;
+    TileLoad<ALPHA> t;
+    t.y0 = lds_u32(st + my_y);
+    t.y1 = lds_u32(st + my_y + w);
+    t.c = lds_u32(st + my_c);
+    if (ALPHA) {
+      t.a0 = lds_u32(st + my_a);
+      t.a1 = lds_u32(st + my_a + w);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+    if (rpg < total_rp) tile_compute_store<CL2, RL2, ALPHA, true>(p, oo, rp, true, t, k, clamp_lo, sbase);
+    // advance to this warp's row pair in the CTA's next band
+    rpg += p.step_rp;
+    rp += p.d_rp;
+    oo += p.dout;
+    if (rp >= rows2) { rp -= rows2; oo += p.wout; }
   }
 }
 
@@ -263,30 +543,140 @@ __global__ void __launch_bounds__(256) k_decode_generic(const DecodeArgs p) {
 static inline bool aligned(const void *p, size_t a) { return ((uintptr_t) p & (a - 1)) == 0; }
 static inline bool aligned(long long v, size_t a) { return ((unsigned long long) v & (a - 1)) == 0; }
 
-constexpr int kDecodeThreads = 1024;
+#ifndef BT709_DECODE_THREADS
+#define BT709_DECODE_THREADS 1024
+#endif
+constexpr int kDecodeThreads = BT709_DECODE_THREADS;
+
+template <int CL2, int RL2, bool ALPHA, bool FULL>
+static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
+  constexpr size_t smem = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
+  auto k = k_decode_fast<CL2, RL2, ALPHA, FULL, kDecodeThreads>;
+  // frames per launch such that every 32-bit unit offset stays below 2^32
+  const unsigned long long lim = 0xFFFF0000ull;
+  unsigned long long per = lim;
+  auto fit = [&](long long stride, unsigned unit, long long frame_bytes) {
+    if (stride <= 0) return;
+    unsigned long long n = (lim * unit - (unsigned long long) frame_bytes) / (unsigned long long) stride + 1;
+    if (n < per) per = n;
+  };
+  fit(a0.sy, 4, (long long) a0.h * a0.py);
+  fit(a0.sc, 4, (long long) a0.rows2 * a0.pc);
+  fit(a0.so, 16, (long long) a0.h * a0.po);
+  if (ALPHA) fit(a0.sa, 4, (long long) a0.h * a0.pa);
+  if (per < 1) per = 1;
+  for (int f0 = 0; f0 < a0.nframes; f0 += (int) per) {
+    DecodeArgs a = a0;
+    a.nframes = (int) ((unsigned long long) (a0.nframes - f0) < per ? (unsigned long long) (a0.nframes - f0) : per);
+    a.y = a0.y + (long long) f0 * a0.sy;
+    a.c = a0.c + (long long) f0 * a0.sc;
+    a.out = a0.out + (long long) f0 * a0.so;
+    if (ALPHA) a.a = a0.a + (long long) f0 * a0.sa;
+    const unsigned total_rp = (unsigned) a.nframes * a.rows2;
+    unsigned grid = (total_rp + a.rps - 1) / a.rps;
+    if (grid > (unsigned) sm_count) grid = sm_count;
+    // per-step increments of the unit offsets, and the extra increment on a frame wrap (mod 2^32)
+    a.step_rp = grid * a.rps;
+    const unsigned d_f = a.step_rp / a.rows2;
+    a.d_rp = a.step_rp - d_f * a.rows2;
+    a.py4 = (unsigned) (a.py / 4); a.pc4 = (unsigned) (a.pc / 4); a.pa4 = (unsigned) (a.pa / 4); a.po16 = (unsigned) (a.po / 16);
+    a.sy4 = (unsigned) (a.sy / 4); a.sc4 = (unsigned) (a.sc / 4); a.sa4 = (unsigned) (a.sa / 4); a.so16 = (unsigned) (a.so / 16);
+    a.dy = d_f * a.sy4 + a.d_rp * 2 * a.py4;
+    a.dc = d_f * a.sc4 + a.d_rp * a.pc4;
+    a.da = d_f * a.sa4 + a.d_rp * 2 * a.pa4;
+    a.dout = d_f * a.so16 + a.d_rp * 2 * a.po16;
+    a.wy = a.sy4 - a.rows2 * 2 * a.py4;
+    a.wc = a.sc4 - a.rows2 * a.pc4;
+    a.wa = a.sa4 - a.rows2 * 2 * a.pa4;
+    a.wout = a.so16 - a.rows2 * 2 * a.po16;
+    k<<<grid, kDecodeThreads, smem, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int) e;
+  }
+  return 0;
+}
+
+constexpr size_t kMaxDynSmem = 232448;  // 227 KB per CTA on sm_100
 
 template <int CL2, int RL2, bool ALPHA>
-static int launch_decode_fast(const DecodeArgs &a, int sm_count, cudaStream_t s) {
-  constexpr size_t smem = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
-  auto k = k_decode_fast<CL2, RL2, ALPHA, kDecodeThreads>;
-  const unsigned total = (unsigned) a.nframes * a.rows2 * a.segs;
-  const unsigned wpc = kDecodeThreads / 32;
-  unsigned grid = (total + wpc - 1) / wpc;
-  if (grid > (unsigned) sm_count) grid = sm_count;
-  k<<<grid, kDecodeThreads, smem, s>>>(a);
-  return (int) cudaGetLastError();
+static bool bulk_ok(const DecodeArgs &a, int *nstages, int *stage_bytes, int *nrows) {
+  constexpr size_t lut = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
+  const int wpc = kDecodeThreads / 32;
+  if (!(a.w % 128 == 0 && a.h % 2 == 0 && a.tiles_per_row <= wpc)) return false;
+  if (!(aligned(a.y, 16) && aligned(a.py, 16) && aligned(a.sy, 16) && aligned(a.c, 16) && aligned(a.pc, 16) &&
+        aligned(a.sc, 16)))
+    return false;
+  if (ALPHA && !(aligned(a.a, 16) && aligned(a.pa, 16) && aligned(a.sa, 16))) return false;
+  *nrows = (ALPHA ? 5 : 3) * a.rps;
+  if (*nrows > a.rps * a.tiles_per_row) return false;  // one producer lane per row
+  *stage_bytes = *nrows * a.w;
+  long long room = (long long) kMaxDynSmem - (long long) lut - 16 * 8 * 2;
+  int n = (int) (room / *stage_bytes);
+  if (n > 8) n = 8;
+  if (n < 2) return false;
+  *nstages = n;
+  return true;
+}
+
+template <int CL2, int RL2, bool ALPHA>
+static int launch_decode_fast(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
+  DecodeArgs a = a0;
+  int nstages = 0, stage_bytes = 0, nrows = 0;
+  // The bulk-staged variant is correct (tests/test_gpu_decode.py runs it) but measured slower than
+  // per-thread loads (774 vs 811 Gpix/s on 600 x 1080p): the path is bound by HBM *write*
+  // bandwidth (profiles/r01_membw_probe.json), not by read latency.  Opt-in for reproduction.
+  static const bool use_bulk = getenv("BT709_BULK") != nullptr;
+  if (use_bulk && bulk_ok<CL2, RL2, ALPHA>(a, &nstages, &stage_bytes, &nrows)) {
+    constexpr size_t lut = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
+    a.nstages = nstages; a.stage_bytes = stage_bytes; a.nrows = nrows;
+    const size_t smem = lut + (size_t) nstages * stage_bytes + (size_t) nstages * 16;
+    // the output offsets are 32-bit in 16-byte units: split batches that would overflow
+    const unsigned long long lim = 0xFFFF0000ull;
+    unsigned long long per = a.so > 0 ? (lim * 16 - (unsigned long long) a.h * a.po) / (unsigned long long) a.so + 1 : lim;
+    if (per < 1) per = 1;
+    for (int f0 = 0; f0 < a0.nframes; f0 += (int) per) {
+      a.nframes = (int) ((unsigned long long) (a0.nframes - f0) < per ? (unsigned long long) (a0.nframes - f0) : per);
+      a.y = a0.y + (long long) f0 * a0.sy;
+      a.c = a0.c + (long long) f0 * a0.sc;
+      a.out = a0.out + (long long) f0 * a0.so;
+      if (ALPHA) a.a = a0.a + (long long) f0 * a0.sa;
+      const unsigned total_rp = (unsigned) a.nframes * a.rows2;
+      unsigned grid = (total_rp + a.rps - 1) / a.rps;
+      if (grid > (unsigned) sm_count) grid = sm_count;
+      a.step_rp = grid * a.rps;
+      const unsigned d_f = a.step_rp / a.rows2;
+      a.d_rp = a.step_rp - d_f * a.rows2;
+      a.po16 = (unsigned) (a.po / 16); a.so16 = (unsigned) (a.so / 16);
+      a.dout = d_f * a.so16 + a.d_rp * 2 * a.po16;
+      a.wout = a.so16 - a.rows2 * 2 * a.po16;
+      k_decode_bulk<CL2, RL2, ALPHA, kDecodeThreads><<<grid, kDecodeThreads, smem, s>>>(a);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return (int) e;
+    }
+    return 0;
+  }
+  const bool full = (a.w % 128 == 0) && (a.h % 2 == 0);
+  return full ? launch_decode_fast2<CL2, RL2, ALPHA, true>(a, sm_count, s)
+              : launch_decode_fast2<CL2, RL2, ALPHA, false>(a, sm_count, s);
 }
 
 int launch_decode(const DecodeArgs &a0, int sm_count, void *stream) {
   cudaStream_t s = (cudaStream_t) stream;
   DecodeArgs a = a0;
   a.rows2 = (a.h + 1) / 2;
-  a.segs = (a.w + 255) / 256;
+  // 128-pixel tiles; the CTA's warps cover rps whole row pairs per step (see k_decode_fast)
+  a.tiles_per_row = (a.w + 127) / 128;
+  const int wpc = kDecodeThreads / 32;
+  a.rps = a.tiles_per_row >= wpc ? 1 : wpc / a.tiles_per_row;
+  a.tile_stride = a.tiles_per_row >= wpc ? wpc : a.tiles_per_row;  // > 4096 px wide: warps loop over tiles
   const bool alpha = a.a != nullptr;
-  const unsigned long long units = (unsigned long long) a.nframes * a.rows2 * a.segs;
+  const unsigned long long units = (unsigned long long) a.nframes * a.rows2 + 2ull * sm_count * 32;
   bool fast = (a.w % 4 == 0) && aligned(a.y, 4) && aligned(a.py, 4) && aligned(a.sy, 4) && aligned(a.c, 4) &&
               aligned(a.pc, 4) && aligned(a.sc, 4) && aligned(a.out, 16) && aligned(a.po, 16) &&
-              aligned(a.so, 16) && units < 0x7FFFFFFFull && (a.cells_log2 == 10 || a.cells_log2 == 12);
+              aligned(a.so, 16) && units < 0x7FFFFFFFull && a.sy < (1ll << 32) && a.sc < (1ll << 32) &&
+              a.so < (1ll << 34) && a.sa < (1ll << 32) && a.py < (1ll << 28) && a.pc < (1ll << 28) && a.po < (1ll << 30) &&
+              a.pa < (1ll << 28) && a.sy >= 0 && a.sc >= 0 && a.so >= 0 && a.sa >= 0 &&
+              (a.cells_log2 == 10 || a.cells_log2 == 12);
   if (alpha) fast = fast && aligned(a.a, 4) && aligned(a.pa, 4) && aligned(a.sa, 4);
   if (fast) {
     if (a.cells_log2 == 10)
@@ -554,7 +944,13 @@ int launch_copy_packed(const CopyPackedArgs &a, void *stream) {
 template <int CL2, int RL2, bool ALPHA>
 static int optin_decode_smem() {
   constexpr size_t smem = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
-  return (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, kDecodeThreads>,
+  int e = (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, true, kDecodeThreads>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_bulk<CL2, RL2, ALPHA, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  return (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, false, kDecodeThreads>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 }
 

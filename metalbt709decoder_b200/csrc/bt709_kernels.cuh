@@ -14,7 +14,17 @@ struct DecodeArgs {
   long long sy, sc, sa, so;  // frame strides, bytes
   int w, h, nframes;
   int rows2;            // ceil(h / 2) row pairs per frame
-  int segs;             // 256-pixel segments per row pair (fast kernel)
+  int tiles_per_row;    // 256-pixel tiles per row pair (fast kernel)
+  int rps;              // row pairs a CTA covers per step = 32 / tiles_per_row (>= 1)
+  int tile_stride;      // min(tiles_per_row, 32): warps loop over tiles when a row has more than 32
+  // fast kernel addressing: 32-bit offsets in load/store units (4 B for Y/CbCr/alpha, 16 B for BGRA)
+  unsigned step_rp, d_rp;               // row pairs a CTA band advances per step; its remainder mod rows2
+  unsigned py4, pc4, pa4, po16;         // pitches in units
+  unsigned sy4, sc4, sa4, so16;         // frame strides in units
+  unsigned dy, dc, da, dout;            // offset increment per step
+  unsigned wy, wc, wa, wout;            // extra increment when the row pair wraps into the next frame
+  // bulk-staged kernel: shared-memory ring geometry
+  int nstages, stage_bytes, nrows;      // ring depth; bytes per stage; rows (= bulk copies) per stage
   const uint32_t *lut;  // cell LUT of the selected gamma, N + 1 words, device memory
   float clamp_lo;
   int cells_log2;

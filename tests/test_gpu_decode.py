@@ -167,3 +167,26 @@ def test_uhd_frame_size_independent_properties():
     g = decode(3, y, cn)
     assert np.array_equal(g[..., 0], g[..., 1]) and np.array_equal(g[..., 1], g[..., 2])
     assert (g[..., 3] == 255).all()
+
+
+def test_bulk_staged_variant_matches(tmp_path):
+    """The cp.async.bulk (TMA 1-D) shared-memory-ring variant of the decode kernel is opt-in
+    (BT709_BULK=1, read once per process): run it in a subprocess and compare with the oracle."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, "tests")
+from _oracle import Oracle, frame_random
+from _gpu import decode
+ora = Oracle()
+for (w, h, g) in [(1920, 64, 3), (3840, 8, 0), (2048, 16, 2), (384, 6, 1)]:
+    y, c = frame_random(w, h, seed=5)
+    assert np.array_equal(decode(g, y, c), ora.decode_nv12(g, y, c)), (w, h, g)
+print("bulk ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, BT709_BULK="1")
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "bulk ok" in r.stdout, r.stdout + r.stderr
