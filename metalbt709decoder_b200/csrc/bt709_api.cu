@@ -226,6 +226,7 @@ int bt709_decode_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane
   a.w = w; a.h = h; a.nframes = nframes;
   a.lut = ctx->dec_lut[gamma]; a.clamp_lo = ctx->dec_clamp[gamma]; a.cells_log2 = ctx->dec_cells[gamma];
   a.m = ctx->m;
+  a.one = 1.0f;
   return finish(ctx, launch_decode(a, ctx->sm_count, stream), stream, wait);
 }
 

@@ -141,8 +141,13 @@ __device__ __forceinline__ f32x2 fma2_rz(f32x2 a, f32x2 b, f32x2 c) {
 
 // loop-invariant packed constants {k, k}
 struct DecodeK2 {
-  f32x2 kY, kC, inv255, ys, g_cb, b_cb, r_cr, g_cr, fN, magic;
+  f32x2 kY, kC, inv255, ys, g_cb, b_cb, r_cr, g_cr, fN, magic, one;
 };
+__device__ __forceinline__ f32x2 fma2_rn(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
 
 template <int K>
 __device__ __forceinline__ uint32_t magic_byte(uint32_t word) {  // bits of the float 2^23 + byte K
@@ -170,13 +175,15 @@ __device__ __forceinline__ uint4 decode_row(uint32_t yw, uint32_t aw, f32x2 cb_g
   // luma terms, BT709.h:494 then :424 — pairs (px0, px2) and (px1, px3)
   f32x2 y02 = mul2(mul2(add2(pku(magic_byte<0>(yw), magic_byte<2>(yw)), k.kY), k.inv255), k.ys);
   f32x2 y13 = mul2(mul2(add2(pku(magic_byte<1>(yw), magic_byte<3>(yw)), k.kY), k.inv255), k.ys);
-  float y0, y1, y2, y3, crA, crB, cgA, cgB, cbA, cbB, bgA, bgB;
+  // (Y + Cb) first, then + Cr (BT709.h:425).  ptxas contracts a packed mul.rn.f32x2 feeding an
+  // add.rn.f32x2 into one FFMA2 (a single rounding: not bit-exact), so the packed add is written as
+  // fma(y, one, cb_g) with `one` = 1.0f read from the kernel arguments: y*1 is exact, the sum is
+  // rounded once exactly like an add, and neither multiply can be folded into it.
+  f32x2 g02 = fma2_rn(y02, k.one, cb_g), g13 = fma2_rn(y13, k.one, cb_g);
+  float y0, y1, y2, y3, g0, g1, g2, g3, crA, crB, cgA, cgB, cbA, cbB;
   upk(y02, y0, y2); upk(y13, y1, y3);
-  upk(cr_r, crA, crB); upk(cr_g, cgA, cgB); upk(cb_b, cbA, cbB); upk(cb_g, bgA, bgB);
-  // (Y + Cb) first, then + Cr (BT709.h:425).  Scalar adds on purpose: ptxas contracts a packed
-  // mul.rn.f32x2 feeding an add.rn.f32x2 into FFMA2 (one rounding instead of two), which would
-  // break bit-exactness; it never contracts a packed multiply with a scalar add.rn.
-  const float g0 = __fadd_rn(y0, bgA), g1 = __fadd_rn(y1, bgA), g2 = __fadd_rn(y2, bgB), g3 = __fadd_rn(y3, bgB);
+  upk(g02, g0, g2); upk(g13, g1, g3);
+  upk(cr_r, crA, crB); upk(cr_g, cgA, cgB); upk(cb_b, cbA, cbB);
   uint32_t r0, r1, r2, r3, gg0, gg1, gg2, gg3, b0, b1, b2, b3;
   lut2<CL2, RL2>(add_sat(y0, crA), add_sat(y2, crB), clamp_lo, k, sbase, r0, r2);
   lut2<CL2, RL2>(add_sat(y1, crA), add_sat(y3, crB), clamp_lo, k, sbase, r1, r3);
@@ -257,7 +264,9 @@ __device__ __forceinline__ void tile_compute_store(const DecodeArgs &p, unsigned
                    decode_row<CL2, RL2, ALPHA>(t.y1, t.a1, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
 }
 
-template <int CL2, int RL2, bool ALPHA, bool FULL, int THREADS>
+// WRAP = false: the batch is one contiguous tall image (frame stride == rows * pitch for every
+// plane), so stepping never crosses a frame seam and the carry logic disappears.
+template <int CL2, int RL2, bool ALPHA, bool FULL, bool WRAP, int PD, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) {
   extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = 1 << CL2, R = 1 << RL2;
@@ -280,6 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) 
   k.g_cr = pk(p.m.g_cr, p.m.g_cr);
   k.fN = pk((float) N, (float) N);
   k.magic = pk(8388608.0f, 8388608.0f);
+  k.one = pk(p.one, p.one);
 
   // this warp's place in the CTA's band: fixed for the whole kernel
   const unsigned r_local = warp / p.tiles_per_row;
@@ -295,40 +305,156 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) 
   for (unsigned tile = tile0; tile < (unsigned) p.tiles_per_row; tile += p.tile_stride) {
     const unsigned col4 = tile * 32 + lane;  // column in 4-pixel units
     const bool valid = FULL || (int) (col4 * 4) < p.w;
-    // load offsets (run one step ahead) and store offset
+    // Two offset streams: the load stream runs PD steps ahead of the store stream.  Measured
+    // (tools/probes/gran_bw.cu): with 1024 threads per SM the HBM pipe needs >= 24 B of loads in
+    // flight per thread to reach 6 TB/s at this byte mix; 12 B (one step ahead) gave 4.4 TB/s.
     unsigned oy = f0 * p.sy4 + rp0 * 2 * p.py4 + col4;
     unsigned oc = f0 * p.sc4 + rp0 * p.pc4 + col4;
     unsigned oa = ALPHA ? f0 * p.sa4 + rp0 * 2 * p.pa4 + col4 : 0;
     unsigned oo = f0 * p.so16 + rp0 * 2 * p.po16 + col4;
-    unsigned rp = rp0;  // row pair of the data in A at the top of the loop
-    unsigned left = nsteps;
-    TileLoad<ALPHA> A, B;
-    tile_load<ALPHA, FULL>(p, oy, oc, oa, rp, valid, A);
-    while (true) {
-      // ---- A holds step k; prefetch step k+1 into B
-      unsigned rpn = rp + p.d_rp;
-      const bool wrap_a = rpn >= rows2;
+    unsigned rpl = rp0, rps_ = rp0;  // row pair of the next load / of the next store
+    constexpr int NB = PD + 1;
+    TileLoad<ALPHA> buf[NB];
+    auto advance_load = [&]() {
+      rpl += p.d_rp;
       oy += p.dy; oc += p.dc;
       if (ALPHA) oa += p.da;
-      if (wrap_a) { rpn -= rows2; oy += p.wy; oc += p.wc; if (ALPHA) oa += p.wa; }
-      if (left > 1) tile_load<ALPHA, FULL>(p, oy, oc, oa, rpn, valid, B);
-      tile_compute_store<CL2, RL2, ALPHA, FULL>(p, oo, rp, valid, A, k, clamp_lo, sbase);
-      if (left == 1) break;
-      oo += p.dout;
-      if (wrap_a) oo += p.wout;
-      // ---- B holds step k+1; prefetch step k+2 into A
-      rp = rpn + p.d_rp;
-      const bool wrap_b = rp >= rows2;
-      oy += p.dy; oc += p.dc;
-      if (ALPHA) oa += p.da;
-      if (wrap_b) { rp -= rows2; oy += p.wy; oc += p.wc; if (ALPHA) oa += p.wa; }
-      if (left > 2) tile_load<ALPHA, FULL>(p, oy, oc, oa, rp, valid, A);
-      tile_compute_store<CL2, RL2, ALPHA, FULL>(p, oo, rpn, valid, B, k, clamp_lo, sbase);
-      if (left == 2) break;
-      oo += p.dout;
-      if (wrap_b) oo += p.wout;
-      left -= 2;
+      if (WRAP && rpl >= rows2) { rpl -= rows2; oy += p.wy; oc += p.wc; if (ALPHA) oa += p.wa; }
+    };
+#pragma unroll
+    for (int j = 0; j < PD; j++) {
+      if ((unsigned) j < nsteps) {
+        tile_load<ALPHA, FULL>(p, oy, oc, oa, rpl, valid, buf[j]);
+        advance_load();
+      }
     }
+    unsigned kk = 0;
+    while (true) {
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        if (kk + PD < nsteps) {
+          tile_load<ALPHA, FULL>(p, oy, oc, oa, rpl, valid, buf[(j + PD) % NB]);
+          advance_load();
+        }
+        tile_compute_store<CL2, RL2, ALPHA, FULL>(p, oo, rps_, valid, buf[j], k, clamp_lo, sbase);
+        rps_ += p.d_rp;
+        oo += p.dout;
+        if (WRAP && rps_ >= rows2) { rps_ -= rows2; oo += p.wout; }
+        if (++kk >= nsteps) goto tile_done;
+      }
+    }
+  tile_done:;
+  }
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// ================================================================= decode, cp.async warp ring
+// Same arithmetic and CTA-band layout as k_decode_fast, but each warp stages its own inputs through
+// a private shared-memory ring: per step ONE cp.async instruction (16 bytes per lane; lanes 0-7
+// fetch the 128 B of Y row 0, lanes 8-15 Y row 1, lanes 16-23 the CbCr row) replaces three
+// LDG.32 and their address arithmetic, and the bytes in flight live in shared memory instead of
+// registers (D - 1 steps ahead).  Needs FULL geometry and 16-byte aligned Y / CbCr planes.
+template <int CL2, int RL2, bool ALPHA, bool WRAP, int D, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) {
+  extern __shared__ __align__(128) uint32_t s_lut[];
+  constexpr int N = 1 << CL2, R = 1 << RL2;
+  constexpr uint32_t kLutBytes = (uint32_t) (N + 1) * R * 4;
+  constexpr uint32_t kStage = ALPHA ? 640 : 384;  // Y0 | Y1 | CbCr (| A0 | A1), 128 B each
+  for (int i = threadIdx.x; i < (N + 1) * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_lut);
+  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - (0x4B000000u << (2 + RL2));
+  const uint32_t ring = smem0 + kLutBytes + warp * (D * kStage);
+  const float clamp_lo = p.clamp_lo;
+  DecodeK2 k;
+  k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
+  k.kC = pk(-(8388608.0f + 128.0f), -(8388608.0f + 128.0f));
+  k.inv255 = pk(p.m.inv255, p.m.inv255);
+  k.ys = pk(p.m.ys, p.m.ys);
+  k.g_cb = pk(p.m.g_cb, p.m.g_cb);
+  k.b_cb = pk(p.m.b_cb, p.m.b_cb);
+  k.r_cr = pk(p.m.r_cr, p.m.r_cr);
+  k.g_cr = pk(p.m.g_cr, p.m.g_cr);
+  k.fN = pk((float) N, (float) N);
+  k.magic = pk(8388608.0f, 8388608.0f);
+  k.one = pk(p.one, p.one);
+
+  const unsigned r_local = warp / p.tiles_per_row;
+  if (r_local >= (unsigned) p.rps) return;
+  const unsigned tile = warp - r_local * p.tiles_per_row;
+  const unsigned rows2 = p.rows2;
+  const unsigned total_rp = (unsigned) p.nframes * rows2;
+  const unsigned rpg0 = blockIdx.x * p.rps + r_local;
+  if (rpg0 >= total_rp) return;
+  const unsigned f0 = rpg0 / rows2, rp0 = rpg0 - f0 * rows2;
+  const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;
+
+  // ---- copy role of this lane: which plane row it fetches, as base + 32-bit offset in 4-byte units
+  const int role = lane >> 3, sub = lane & 7;  // 0: Y row 0, 1: Y row 1, 2: CbCr, 3: idle (alpha: second pass)
+  const uint8_t *cbase = role < 2 ? p.y : p.c;
+  unsigned coff = role < 2 ? f0 * p.sy4 + (rp0 * 2 + role) * p.py4 : f0 * p.sc4 + rp0 * p.pc4;
+  coff += tile * 32 + sub * 4;
+  const unsigned cinc = role < 2 ? p.dy : p.dc, cwrap = role < 2 ? p.wy : p.wc;
+  const uint32_t cdst = role * 128 + sub * 16;
+  // alpha rows (ALPHA only): lanes 0-7 row 0, lanes 8-15 row 1, via a second cp.async
+  unsigned aoff = ALPHA ? f0 * p.sa4 + (rp0 * 2 + (role & 1)) * p.pa4 + tile * 32 + sub * 4 : 0;
+  const uint32_t adst = 384 + (role & 1) * 128 + sub * 16;
+  unsigned rpl = rp0;
+
+  auto issue = [&](uint32_t slot) {
+    if (role < 3)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + slot * kStage + cdst),
+                   "l"(ptr_mad(cbase, coff, 4))
+                   : "memory");
+    if (ALPHA && role < 2)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + slot * kStage + adst),
+                   "l"(ptr_mad(p.a, aoff, 4))
+                   : "memory");
+    // step this lane's source to the warp's row pair in the CTA's next band
+    rpl += p.d_rp;
+    coff += cinc;
+    if (ALPHA) aoff += p.da;
+    if (WRAP && rpl >= rows2) { rpl -= rows2; coff += cwrap; if (ALPHA) aoff += p.wa; }
+  };
+
+  const unsigned col4 = tile * 32 + lane;
+  unsigned oo = f0 * p.so16 + rp0 * 2 * p.po16 + col4;
+  unsigned rps_ = rp0;
+#pragma unroll
+  for (int j = 0; j < D - 1; j++) {
+    if ((unsigned) j < nsteps) issue(j);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  uint32_t slot = 0, fill = D - 1;
+  for (unsigned kk = 0; kk < nsteps; kk++) {
+    if (kk + D - 1 < nsteps) issue(fill);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+    __syncwarp();
+    const uint32_t st = ring + slot * kStage + lane * 4;
+    TileLoad<ALPHA> t;
+    t.y0 = lds_u32(st);
+    t.y1 = lds_u32(st + 128);
+    t.c = lds_u32(st + 256);
+    if (ALPHA) {
+      t.a0 = lds_u32(st + 384);
+      t.a1 = lds_u32(st + 512);
+    }
+    __syncwarp();  // every lane has its words before this slot is refilled
+    tile_compute_store<CL2, RL2, ALPHA, true>(p, oo, rps_, true, t, k, clamp_lo, sbase);
+    rps_ += p.d_rp;
+    oo += p.dout;
+    if (WRAP && rps_ >= rows2) { rps_ -= rows2; oo += p.wout; }
+    slot = slot + 1 == D ? 0 : slot + 1;
+    fill = fill + 1 == D ? 0 : fill + 1;
   }
 }
 
@@ -374,11 +500,6 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
 
 template <int CL2, int RL2, bool ALPHA, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_decode_bulk(const DecodeArgs p) {
@@ -416,6 +537,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_bulk(const DecodeArgs p) 
   k.g_cr = pk(p.m.g_cr, p.m.g_cr);
   k.fN = pk((float) N, (float) N);
   k.magic = pk(8388608.0f, 8388608.0f);
+  k.one = pk(p.one, p.one);
 
   if (warp >= nwarps_active) return;  // spare warps
   const unsigned rows2 = p.rows2, rps = p.rps, w = p.w;
@@ -547,11 +669,25 @@ static inline bool aligned(long long v, size_t a) { return ((unsigned long long)
 #define BT709_DECODE_THREADS 1024
 #endif
 constexpr int kDecodeThreads = BT709_DECODE_THREADS;
+#ifndef BT709_PREFETCH_DEPTH
+#define BT709_PREFETCH_DEPTH 3
+#endif
+constexpr int kPrefetchDepth = BT709_PREFETCH_DEPTH;  // steps the loads run ahead of the math
+#ifndef BT709_RING_DEPTH
+#define BT709_RING_DEPTH 2
+#endif
+constexpr int kRingDepth = BT709_RING_DEPTH;  // stages of the per-warp cp.async ring
 
-template <int CL2, int RL2, bool ALPHA, bool FULL>
+template <int CL2, int RL2, bool ALPHA, bool FULL, bool WRAP>
 static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
   constexpr size_t smem = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
-  auto k = k_decode_fast<CL2, RL2, ALPHA, FULL, kDecodeThreads>;
+  auto k = k_decode_fast<CL2, RL2, ALPHA, FULL, WRAP, kPrefetchDepth, kDecodeThreads>;
+  auto kring = k_decode_ring<CL2, RL2, ALPHA, WRAP, kRingDepth, kDecodeThreads>;
+  constexpr size_t smem_ring = smem + (size_t) (kDecodeThreads / 32) * kRingDepth * (ALPHA ? 640 : 384);
+  static const bool no_ring = getenv("BT709_NO_RING") != nullptr;
+  const bool use_ring = FULL && !no_ring && aligned(a0.y, 16) && aligned(a0.py, 16) && aligned(a0.sy, 16) &&
+                        aligned(a0.c, 16) && aligned(a0.pc, 16) && aligned(a0.sc, 16) &&
+                        (!ALPHA || (aligned(a0.a, 16) && aligned(a0.pa, 16) && aligned(a0.sa, 16)));
   // frames per launch such that every 32-bit unit offset stays below 2^32
   const unsigned long long lim = 0xFFFF0000ull;
   unsigned long long per = lim;
@@ -565,6 +701,27 @@ static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t 
   fit(a0.so, 16, (long long) a0.h * a0.po);
   if (ALPHA) fit(a0.sa, 4, (long long) a0.h * a0.pa);
   if (per < 1) per = 1;
+  if (a0.nframes == 1) {
+    // one (possibly very tall) image: split by rows instead, in chunks whose offsets fit in 32 bits
+    const unsigned long long out_bytes = (unsigned long long) a0.h * a0.po;
+    if (out_bytes > lim * 16 || (unsigned long long) a0.h * a0.py > lim * 4) {
+      long long rows_per = (long long) ((lim * 16) / (unsigned long long) a0.po);
+      if ((unsigned long long) rows_per * a0.py > lim * 4) rows_per = (long long) ((lim * 4) / (unsigned long long) a0.py);
+      rows_per &= ~1ll;
+      for (long long r0 = 0; r0 < a0.h; r0 += rows_per) {
+        DecodeArgs a = a0;
+        a.h = (int) (a0.h - r0 < rows_per ? a0.h - r0 : rows_per);
+        a.rows2 = (a.h + 1) / 2;
+        a.y = a0.y + r0 * a0.py;
+        a.c = a0.c + (r0 / 2) * a0.pc;
+        a.out = a0.out + r0 * a0.po;
+        if (ALPHA) a.a = a0.a + r0 * a0.pa;
+        int e = launch_decode_fast2<CL2, RL2, ALPHA, FULL, WRAP>(a, sm_count, s);
+        if (e) return e;
+      }
+      return 0;
+    }
+  }
   for (int f0 = 0; f0 < a0.nframes; f0 += (int) per) {
     DecodeArgs a = a0;
     a.nframes = (int) ((unsigned long long) (a0.nframes - f0) < per ? (unsigned long long) (a0.nframes - f0) : per);
@@ -589,7 +746,10 @@ static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t 
     a.wc = a.sc4 - a.rows2 * a.pc4;
     a.wa = a.sa4 - a.rows2 * 2 * a.pa4;
     a.wout = a.so16 - a.rows2 * 2 * a.po16;
-    k<<<grid, kDecodeThreads, smem, s>>>(a);
+    if (use_ring)
+      kring<<<grid, kDecodeThreads, smem_ring, s>>>(a);
+    else
+      k<<<grid, kDecodeThreads, smem, s>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int) e;
   }
@@ -656,8 +816,17 @@ static int launch_decode_fast(const DecodeArgs &a0, int sm_count, cudaStream_t s
     return 0;
   }
   const bool full = (a.w % 128 == 0) && (a.h % 2 == 0);
-  return full ? launch_decode_fast2<CL2, RL2, ALPHA, true>(a, sm_count, s)
-              : launch_decode_fast2<CL2, RL2, ALPHA, false>(a, sm_count, s);
+  if (!full) return launch_decode_fast2<CL2, RL2, ALPHA, false, true>(a, sm_count, s);
+  // contiguous frames: decode the batch as one tall image (no frame seams to step across)
+  const bool contiguous = a.nframes == 1 || (a.sy == (long long) a.h * a.py && a.sc == (long long) a.rows2 * a.pc &&
+                                             a.so == (long long) a.h * a.po && (!ALPHA || a.sa == (long long) a.h * a.pa));
+  if (contiguous && (long long) a.nframes * a.h < (1ll << 30)) {
+    a.h *= a.nframes;
+    a.rows2 *= a.nframes;
+    a.nframes = 1;
+    return launch_decode_fast2<CL2, RL2, ALPHA, true, false>(a, sm_count, s);
+  }
+  return launch_decode_fast2<CL2, RL2, ALPHA, true, true>(a, sm_count, s);
 }
 
 int launch_decode(const DecodeArgs &a0, int sm_count, void *stream) {
@@ -944,13 +1113,22 @@ int launch_copy_packed(const CopyPackedArgs &a, void *stream) {
 template <int CL2, int RL2, bool ALPHA>
 static int optin_decode_smem() {
   constexpr size_t smem = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
-  int e = (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, true, kDecodeThreads>,
+  int e = (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, true, true, kPrefetchDepth, kDecodeThreads>,
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, true, false, kPrefetchDepth, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_ring<CL2, RL2, ALPHA, true, kRingDepth, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_ring<CL2, RL2, ALPHA, false, kRingDepth, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
   if (e) return e;
   e = (int) cudaFuncSetAttribute(k_decode_bulk<CL2, RL2, ALPHA, kDecodeThreads>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
   if (e) return e;
-  return (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, false, kDecodeThreads>,
+  return (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, false, true, kPrefetchDepth, kDecodeThreads>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 }
 

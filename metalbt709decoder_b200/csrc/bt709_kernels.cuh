@@ -29,6 +29,7 @@ struct DecodeArgs {
   float clamp_lo;
   int cells_log2;
   MatrixConsts m;
+  float one;  // 1.0f, deliberately a runtime value (see decode_row)
 };
 
 struct RescaleArgs {
