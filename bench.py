@@ -109,12 +109,14 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kind):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def ncu_traffic(kind, pixels_per_launch):
+    """DRAM bytes per launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum of the
+    committed `ncu --set full` capture (profiles/traffic.json, bytes per pixel) scaled to this launch."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get(kind)
+            bpp = json.load(open(p)).get(kind + "_bytes_per_pixel")
+            return None if bpp is None else bpp * pixels_per_launch
         except Exception:
             return None
     return None
@@ -328,7 +330,7 @@ def run_b200(args):
                        "frames_per_gpu": frames, "l2": "inputs+outputs per step >> 126 MB L2; no flush needed",
                        "fps": all_units / (w * h) / secs, "parallelism": f"frame-sharded x{world}, no collective"},
             "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic(kind), "peak_source": peak_src,
+                         "traffic": ncu_traffic(kind, float(frames) * w * h / launches_per_step), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algorithmic_bytes(kind, w, h, frames) / launches_per_step,
                          "avg_launch_ms": avg_launch_s * 1e3, "kernels_per_step": launches_per_step},
             "cpu_baseline": cpu,
