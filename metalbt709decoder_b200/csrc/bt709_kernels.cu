@@ -1024,11 +1024,194 @@ __global__ void __launch_bounds__(256) k_encode(const EncodeArgs p) {
   }
 }
 
+// ------------------------------------------------------------------------- encode, fast
+// Same arithmetic as k_encode, organised like the decode: persistent CTAs of 1024 threads, a warp
+// owns a 128-pixel x 2-row tile (lane l: pixels 4l..4l+3 of both rows = two 2x2 blocks), the warps
+// of a CTA cover whole row pairs (bands), addresses are 32-bit unit offsets.  Per warp step:
+// 2 x LDG.128 (512 B per row), 2 x STG.32 of Y (128 B per row), 1 x STG.32 of CbCr (128 B).
+//   * both 256-entry byte tables are merged into one {linear, requantised/255} float2 table,
+//     replicated 16x in shared memory so the LDS.64 gathers are conflict-free per half-warp;
+//   * float32 steps run two at a time on the packed FADD2/FMUL2/FFMA2 pipe.  ptxas contracts a
+//     packed multiply feeding a packed add into one FFMA2 (one rounding instead of two), so every
+//     add that follows a multiply is written fma(product, one, addend) with a run-time 1.0;
+//   * x / 1.8556f and x / 1.5748f are q0 = x*rc; r = fma(-q0, c, x); q = fma(r, rc, q0), which equals
+//     the IEEE quotient for every value this path can produce (all 2^24 8-bit RGB triples checked
+//     on the host: tests/test_tables_cpu.py) and costs 3 instructions instead of ~10;
+//   * round() of the positive results is add.rz(+0.5) then add.rz(+2^23): the code is the low byte.
+struct EncK {
+  f32x2 one, kr, kg, kb, s219, o16, s224, o128, rcb, ncb, rcr, ncr, quarter, half, magic, inv255, nmagic;
+};
+
+__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// exact a + b where a (or b) may be the result of a packed multiply: never contracted
+__device__ __forceinline__ f32x2 add2_nc(f32x2 a, f32x2 b, const EncK &k) { return fma2_rn(a, k.one, b); }
+
+// Ey of BT709.h:223 for two pixels, then round(Ey*219 + 16) (BT709.h:234, 245): magic floats 2^23 + Y
+__device__ __forceinline__ f32x2 enc_luma2(f32x2 rn, f32x2 gn, f32x2 bn, const EncK &k) {
+  f32x2 ey = add2_nc(add2_nc(mul2(k.kr, rn), mul2(k.kg, gn), k), mul2(k.kb, bn), k);
+  f32x2 ay = add2_nc(mul2(ey, k.s219), k.o16, k);
+  return add2_rz(add2_rz(ay, k.half), k.magic);
+}
+
+template <bool WRAP>
+__global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  // [0, 32 KB): float2 table, entry b replica r at byte b*128 + r*8;  then the chroma cell LUT
+  float2 *s_tab = reinterpret_cast<float2 *>(s_mem);
+  uint32_t *s_olut = s_mem + 256 * 32;
+  const int nl = (1 << p.out_cells_log2) + 1;
+  for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
+    const int b = i >> 4;
+    s_tab[i] = make_float2(__ldg(&p.lin256[b]), __ldg(&p.compn256[b]));
+  }
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) s_olut[i] = __ldg(&p.out_lut[i]);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t tab = (uint32_t) __cvta_generic_to_shared(s_tab) + ((lane & 15) << 3);
+  const uint32_t olut = (uint32_t) __cvta_generic_to_shared(s_olut) - (0x4B000000u << 2);
+  const float clamp_lo = p.out_clamp_lo;
+  const float fN = (float) (1 << p.out_cells_log2);
+  EncK k;
+  auto bc = [](float v) { return pk(v, v); };
+  k.one = bc(p.one); k.kr = bc(0.2126f); k.kg = bc(0.7152f); k.kb = bc(0.0722f);
+  k.s219 = bc(219.0f); k.o16 = bc(16.0f); k.s224 = bc(224.0f); k.o128 = bc(128.0f);
+  k.rcb = bc(1.0f / 1.8556f); k.ncb = bc(-1.8556f); k.rcr = bc(1.0f / 1.5748f); k.ncr = bc(-1.5748f);
+  k.quarter = bc(0.25f); k.half = bc(0.5f); k.magic = bc(8388608.0f); k.nmagic = bc(-8388608.0f);
+  k.inv255 = bc(1.0f / 255.0f);
+
+  const unsigned r_local = warp / p.tiles_per_row;
+  if (r_local >= (unsigned) p.rps) return;
+  const unsigned tile = warp - r_local * p.tiles_per_row;
+  const unsigned rows2 = p.h / 2;
+  const unsigned total_rp = (unsigned) p.nframes * rows2;
+  const unsigned rpg0 = blockIdx.x * p.rps + r_local;
+  if (rpg0 >= total_rp) return;
+  const unsigned f0 = rpg0 / rows2, rp0 = rpg0 - f0 * rows2;
+  const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;
+  const unsigned col4 = tile * 32 + lane;
+  unsigned oi = f0 * p.si16 + rp0 * 2 * p.pi16 + col4;  // BGRA in, 16-byte units
+  unsigned oy = f0 * p.sy4 + rp0 * 2 * p.py4 + col4;    // Y out, 4-byte units
+  unsigned oc = f0 * p.sc4 + rp0 * p.pc4 + col4;        // CbCr out, 4-byte units
+  unsigned rp = rp0;
+
+  auto fetch = [&](uint32_t px, int shift, float &lin, float &cn) {
+    // byte -> table address: (byte << 7); the shift-and-mask is one SHF/LOP pair
+    const uint32_t off = shift >= 7 ? ((px >> (shift - 7)) & 0x7F80u) : ((px << 7) & 0x7F80u);
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(tab + off));
+    lin = v.x;
+    cn = v.y;
+  };
+  auto code_of = [&](float mean) -> float {  // BT709_from_linear code as a magic float 2^23 + code
+    float xc = fmaxf(mean, clamp_lo), t;
+    asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(t) : "f"(xc), "f"(fN));
+    uint32_t e;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((__float_as_uint(t) << 2) + olut));
+    return __uint_as_float(__byte_perm(e + __float_as_uint(xc), 0x4B000000u, 0x7543));
+  };
+
+  for (unsigned kk = 0; kk < nsteps; kk++) {
+    const uint4 a = ld_stream_u128(ptr_mad(p.in, oi, 16));
+    const uint4 b = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
+    // Walk the four pixel pairs in the order NW, NE (row 0), SW, SE (row 1): pair (0,2) holds the
+    // west pixels of blocks A and B, pair (1,3) the east pixels.  Luma is finished per pair; the
+    // linear-light sums accumulate in the reference's order ((NW + NE) + SW) + SE (BT709.h:1182-1183).
+    uint32_t yw[2];
+    f32x2 sum[3];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const uint32_t p0 = r ? b.x : a.x, p1 = r ? b.y : a.y, p2 = r ? b.z : a.z, p3 = r ? b.w : a.w;
+      f32x2 m[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {  // e = 0: pixels (0,2); e = 1: pixels (1,3)
+        const uint32_t pw = e ? p1 : p0, pe = e ? p3 : p2;
+        float lw[3], cw_[3], le[3], ce[3];
+        fetch(pw, 16, lw[0], cw_[0]); fetch(pw, 8, lw[1], cw_[1]); fetch(pw, 0, lw[2], cw_[2]);
+        fetch(pe, 16, le[0], ce[0]); fetch(pe, 8, le[1], ce[1]); fetch(pe, 0, le[2], ce[2]);
+        m[e] = enc_luma2(pk(cw_[0], ce[0]), pk(cw_[1], ce[1]), pk(cw_[2], ce[2]), k);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          const f32x2 v = pk(lw[ch], le[ch]);
+          sum[ch] = (r == 0 && e == 0) ? v : add2(sum[ch], v);
+        }
+      }
+      uint32_t y0, y1, y2, y3;
+      upku(m[0], y0, y2); upku(m[1], y1, y3);
+      yw[r] = __byte_perm(__byte_perm(y0, y1, 0x0040), __byte_perm(y2, y3, 0x0040), 0x5410);
+    }
+    // ---- chroma of blocks A and B: mean, requantise to 8 bits in the output gamma
+    // (BT709.h:1418-1420), back to unorm (sRGB.h:32-36)
+    f32x2 q[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      float mA, mB;
+      upk(mul2(sum[ch], k.quarter), mA, mB);
+      q[ch] = mul2(add2(pk(code_of(mA), code_of(mB)), k.nmagic), k.inv255);
+    }
+    f32x2 ey = add2_nc(add2_nc(mul2(k.kr, q[0]), mul2(k.kg, q[1]), k), mul2(k.kb, q[2]), k);
+    f32x2 xb = add2(q[2], mul2(ey, bc(-1.0f))), xr = add2(q[0], mul2(ey, bc(-1.0f)));
+    f32x2 qb = mul2(xb, k.rcb), qr = mul2(xr, k.rcr);
+    qb = fma2_rn(fma2_rn(qb, k.ncb, xb), k.rcb, qb);
+    qr = fma2_rn(fma2_rn(qr, k.ncr, xr), k.rcr, qr);
+    f32x2 mb = add2_rz(add2_rz(add2_nc(mul2(qb, k.s224), k.o128, k), k.half), k.magic);
+    f32x2 mr = add2_rz(add2_rz(add2_nc(mul2(qr, k.s224), k.o128, k), k.half), k.magic);
+    uint32_t cbA, cbB, crA, crB;
+    upku(mb, cbA, cbB); upku(mr, crA, crB);
+    const uint32_t cw = __byte_perm(__byte_perm(cbA, crA, 0x0040), __byte_perm(cbB, crB, 0x0040), 0x5410);
+    st_stream_u32((void *) ptr_mad(p.y, oy, 4), yw[0]);
+    st_stream_u32((void *) ptr_mad(p.y, oy + p.py4, 4), yw[1]);
+    st_stream_u32((void *) ptr_mad(p.c, oc, 4), cw);
+    rp += p.d_rp;
+    oi += p.di; oy += p.dy; oc += p.dc;
+    if (WRAP && rp >= rows2) { rp -= rows2; oi += p.wi; oy += p.wy; oc += p.wc; }
+  }
+}
+
+static int launch_encode_fast(const EncodeArgs &a0, int sm_count, cudaStream_t s) {
+  EncodeArgs a = a0;
+  const int rows2 = a.h / 2;
+  const int wpc = 32;
+  a.tiles_per_row = a.w / 128;
+  a.rps = wpc / a.tiles_per_row;
+  const bool contiguous = a.nframes == 1 || (a.si == (long long) a.h * a.pi && a.sy == (long long) a.h * a.py &&
+                                             a.sc == (long long) rows2 * a.pc);
+  bool wrap = true;
+  if (contiguous) { a.h *= a.nframes; a.nframes = 1; wrap = false; }
+  const unsigned total_rp = (unsigned) a.nframes * (a.h / 2);
+  unsigned grid = (total_rp + a.rps - 1) / a.rps;
+  if (grid > (unsigned) sm_count) grid = sm_count;
+  a.step_rp = grid * a.rps;
+  const unsigned r2 = a.h / 2, d_f = a.step_rp / r2;
+  a.d_rp = a.step_rp - d_f * r2;
+  a.pi16 = (unsigned) (a.pi / 16); a.py4 = (unsigned) (a.py / 4); a.pc4 = (unsigned) (a.pc / 4);
+  a.si16 = (unsigned) (a.si / 16); a.sy4 = (unsigned) (a.sy / 4); a.sc4 = (unsigned) (a.sc / 4);
+  a.di = d_f * a.si16 + a.d_rp * 2 * a.pi16; a.dy = d_f * a.sy4 + a.d_rp * 2 * a.py4; a.dc = d_f * a.sc4 + a.d_rp * a.pc4;
+  a.wi = a.si16 - r2 * 2 * a.pi16; a.wy = a.sy4 - r2 * 2 * a.py4; a.wc = a.sc4 - r2 * a.pc4;
+  a.one = 1.0f;
+  const size_t smem = 32768 + ((size_t) (1 << a.out_cells_log2) + 1) * 4;
+  if (wrap)
+    k_encode_fast<true><<<grid, 1024, smem, s>>>(a);
+  else
+    k_encode_fast<false><<<grid, 1024, smem, s>>>(a);
+  return (int) cudaGetLastError();
+}
+
 int launch_encode(const EncodeArgs &a, int sm_count, void *stream) {
   cudaStream_t s = (cudaStream_t) stream;
   const size_t smem = (512 + (size_t) (1 << a.out_cells_log2) + 1) * 4;
   const bool vec = (a.w % 4 == 0) && aligned(a.in, 16) && aligned(a.pi, 16) && aligned(a.si, 16) && aligned(a.y, 4) &&
                    aligned(a.py, 4) && aligned(a.sy, 4) && aligned(a.c, 4) && aligned(a.pc, 4) && aligned(a.sc, 4);
+  // fast path: whole 128-pixel tiles, at most 32 tiles per row, offsets that fit 32-bit units
+  const unsigned long long in_bytes = (unsigned long long) a.nframes * (a.si > 0 ? a.si : (long long) a.h * a.pi);
+  if (vec && a.w % 128 == 0 && a.w <= 4096 && in_bytes < 0xFFFF0000ull * 16 && a.si >= 0 && a.sy >= 0 && a.sc >= 0 &&
+      a.out_cells_log2 <= 13)
+    return launch_encode_fast(a, sm_count, s);
   const long long n = (long long) a.nframes * (a.h / 2) * (vec ? a.w / 4 : a.w / 2);
   long long grid = (n + 255) / 256;
   if (grid > (long long) sm_count * 8) grid = (long long) sm_count * 8;
@@ -1136,6 +1319,8 @@ static int optin_decode_smem() {
 // dynamic shared memory for the replicated-LUT decode kernels
 int kernels_init() {
   int e;
+  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8193 * 4))) return e;
+  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8193 * 4))) return e;
   if ((e = optin_decode_smem<10, 5, false>())) return e;
   if ((e = optin_decode_smem<10, 5, true>())) return e;
   if ((e = optin_decode_smem<12, 3, false>())) return e;

@@ -54,6 +54,10 @@ struct EncodeArgs {
   const uint32_t *out_lut;  // linear float -> output-gamma byte (cell LUT, BT709_from_linear)
   float out_clamp_lo;
   int out_cells_log2;
+  // fast kernel: band layout and 32-bit unit offsets (16 B for BGRA, 4 B for Y / CbCr), see k_encode_fast
+  int tiles_per_row, rps;
+  unsigned step_rp, d_rp, pi16, py4, pc4, si16, sy4, sc4, di, dy, dc, wi, wy, wc;
+  float one;  // 1.0f, deliberately a runtime value
 };
 
 struct Packed444Args {
