@@ -91,6 +91,14 @@ BT709_API const char *bt709_status_string(int status);
 /* Number of kernels launched through this context since creation (bench accounting). */
 BT709_API unsigned long long bt709_launch_count(const bt709_ctx *ctx);
 
+/* Host-only self-check of the constant tables (needs no GPU; used by tests/test_tables_cpu.py):
+ *   1. for every gamma mode and every one of the 2^24 (Y,Cb,Cr) inputs, the cell-LUT lookup of the
+ *      G-channel matrix output equals the direct double-precision evaluation of the curve;
+ *   2. the three-instruction constant division of the encode path equals IEEE division for every
+ *      8-bit RGB triple.
+ * Returns 0 on success, else the 1-based index of the first failing check. */
+BT709_API int bt709_selftest_host(void);
+
 /* Pass 1.  Replaces -[MetalBT709Decoder decodeBT709:alphaPixelBuffer:bgraSRGBTexture:
  * commandBuffer:renderPassDescriptor:renderWidth:renderHeight:waitUntilCompleted:]
  * (MetalBT709Decoder.h:65-72, .m:217-545) and the kernels/fragments of

@@ -65,6 +65,7 @@ PROTOTYPES = {
     "bt709_last_cuda_error": (c_int, [c_void_p]),
     "bt709_status_string": (ctypes.c_char_p, [c_int]),
     "bt709_launch_count": (ctypes.c_ulonglong, [c_void_p]),
+    "bt709_selftest_host": (c_int, []),
     "bt709_decode_nv12": (c_int, [c_void_p, c_int, PP, PP, PP, PP, c_int, c_int, c_int, c_void_p, c_int]),
     "bt709_rescale_bgra": (c_int, [c_void_p, PP, c_int, c_int, PP, c_int, c_int, c_int, c_void_p, c_int]),
     "bt709_decode_rescale_nv12": (c_int, [c_void_p, c_int, PP, PP, PP, PP, PP, c_int, c_int, c_int, c_int, c_int,

@@ -184,6 +184,8 @@ void bt709_ctx_destroy(bt709_ctx *ctx) {
   delete ctx;
 }
 
+int bt709_selftest_host(void) { return selftest_host(); }
+
 int bt709_ctx_device(const bt709_ctx *ctx) { return ctx ? ctx->device : -1; }
 int bt709_last_cuda_error(const bt709_ctx *ctx) { return ctx ? ctx->last_cuda_error.load() : 0; }
 unsigned long long bt709_launch_count(const bt709_ctx *ctx) { return ctx ? ctx->launches.load() : 0; }
@@ -250,6 +252,7 @@ int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, in
   a.scale_y = (float) in_h / (float) out_h;
   a.lin256 = ctx->lin256[kSrgb];
   a.enc_lut = ctx->fl_lut[kSrgb]; a.enc_clamp_lo = ctx->fl_clamp[kSrgb]; a.enc_cells_log2 = ctx->fl_cells[kSrgb];
+  a.one = 1.0f;
   return finish(ctx, launch_rescale(a, ctx->sm_count, stream), stream, wait);
 }
 

@@ -42,6 +42,7 @@ struct RescaleArgs {
   const uint32_t *enc_lut;  // linear float -> sRGB byte (cell LUT)
   float enc_clamp_lo;
   int enc_cells_log2;
+  float one;  // 1.0f, deliberately a runtime value (blocks FFMA2 contraction, see k_rescale_cols)
 };
 
 struct EncodeArgs {

@@ -203,3 +203,68 @@ MatrixConsts matrix_consts() {
 }
 
 }  // namespace bt709
+
+// ---------------------------------------------------------------- host self-test
+#include <atomic>
+#include <thread>
+#include <vector>
+
+namespace bt709 {
+
+int selftest_host() {
+  const MatrixConsts m = matrix_consts();
+  // 1. cell LUT == direct evaluation on every possible G-channel matrix output, all four gammas
+  for (int g = 0; g < 4; g++) {
+    StepFn fn;
+    CellLut lut;
+    if (!build_step_fn(decode_code, g, &fn)) return 1;
+    if (!build_cell_lut(fn, g == kLinear ? 12 : 10, &lut)) return 2;
+    std::atomic<long> bad(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < 8; t++)
+      th.emplace_back([&, t] {
+        long b = 0;
+        for (int Y = t * 32; Y < (t + 1) * 32; Y++) {
+          const float yt = ((Y - 16) * m.inv255) * m.ys;
+          for (int Cb = 0; Cb < 256; Cb++) {
+            const float cbg = ((Cb - 128) * m.inv255) * m.g_cb;
+            for (int Cr = 0; Cr < 256; Cr++) {
+              float x = (yt + cbg) + ((Cr - 128) * m.inv255) * m.g_cr;
+              x = x < 0.f ? 0.f : (x > 1.f ? 1.f : x);
+              if (cell_lut_eval(lut, x) != decode_code(g, x)) b++;
+            }
+          }
+        }
+        bad += b;
+      });
+    for (auto &x : th) x.join();
+    if (bad.load()) return 3;
+  }
+  // 2. x / c == fma(fma(-q0, c, x), rc, q0), q0 = x * rc, for every value the 4:2:0 encode divides
+  {
+    const float Kr = 0.2126f, Kg = 0.7152f, Kb = 0.0722f, cb = 1.8556f, cr = 1.5748f;
+    const float rcb = 1.0f / cb, rcr = 1.0f / cr;
+    std::atomic<long> bad(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < 8; t++)
+      th.emplace_back([&, t] {
+        long b = 0;
+        for (int R = t * 32; R < (t + 1) * 32; R++)
+          for (int G = 0; G < 256; G++)
+            for (int B = 0; B < 256; B++) {
+              const float rn = R * (1.0f / 255.0f), gn = G * (1.0f / 255.0f), bn = B * (1.0f / 255.0f);
+              const float ey = (Kr * rn) + (Kg * gn) + (Kb * bn);
+              const float xb = bn - ey, xr = rn - ey;
+              const float q0 = xb * rcb, p0 = xr * rcr;
+              if (std::fmaf(std::fmaf(-q0, cb, xb), rcb, q0) != xb / cb) b++;
+              if (std::fmaf(std::fmaf(-p0, cr, xr), rcr, p0) != xr / cr) b++;
+            }
+        bad += b;
+      });
+    for (auto &x : th) x.join();
+    if (bad.load()) return 4;
+  }
+  return 0;
+}
+
+}  // namespace bt709

@@ -68,4 +68,7 @@ struct MatrixConsts {
 };
 MatrixConsts matrix_consts();
 
+// host-only exhaustive self-check (bt709_selftest_host in the C ABI)
+int selftest_host();
+
 }  // namespace bt709
