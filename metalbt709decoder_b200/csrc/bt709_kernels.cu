@@ -1173,8 +1173,9 @@ __global__ void __launch_bounds__(256) k_encode(const EncodeArgs p) {
 // owns a 128-pixel x 2-row tile (lane l: pixels 4l..4l+3 of both rows = two 2x2 blocks), the warps
 // of a CTA cover whole row pairs (bands), addresses are 32-bit unit offsets.  Per warp step:
 // 2 x LDG.128 (512 B per row), 2 x STG.32 of Y (128 B per row), 1 x STG.32 of CbCr (128 B).
-//   * both 256-entry byte tables are merged into one {linear, requantised/255} float2 table,
-//     replicated 16x in shared memory so the LDS.64 gathers are conflict-free per half-warp;
+//   * both 256-entry byte tables are merged into one {linear, requantised/255} float2 table with one
+//     8-byte replica per lane (entry stride 256 B), so the LDS.64 gathers are conflict-free and the
+//     address (byte << 8) | (lane << 3) is a single PRMT of the pixel word and the lane register;
 //   * float32 steps run two at a time on the packed FADD2/FMUL2/FFMA2 pipe.  ptxas contracts a
 //     packed multiply feeding a packed add into one FFMA2 (one rounding instead of two), so every
 //     add that follows a multiply is written fma(product, one, addend) with a run-time 1.0;
@@ -1204,21 +1205,24 @@ __device__ __forceinline__ f32x2 enc_luma2(f32x2 rn, f32x2 gn, f32x2 bn, const E
 template <bool WRAP>
 __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
-  // [0, 32 KB): float2 table, entry b replica r at byte b*128 + r*8;  then the chroma cell LUT
+  // [0, 64 KB): float2 table, entry b replica r at byte b*256 + r*8;  then the chroma cell LUT
   float2 *s_tab = reinterpret_cast<float2 *>(s_mem);
-  uint32_t *s_olut = s_mem + 256 * 32;
+  uint32_t *s_olut = s_mem + 256 * 64;
   const int nl = (1 << p.out_cells_log2) + 1;
-  for (int i = threadIdx.x; i < 256 * 16; i += blockDim.x) {
-    const int b = i >> 4;
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+    const int b = i >> 5;
     s_tab[i] = make_float2(__ldg(&p.lin256[b]), __ldg(&p.compn256[b]));
   }
-  for (int i = threadIdx.x; i < nl; i += blockDim.x) s_olut[i] = __ldg(&p.out_lut[i]);
+  // chroma cell LUT replicated 8x (entry i replica r at word i*8 + r): random means otherwise
+  // cost ~3 wavefronts per lookup and the kernel is bound by shared-memory bandwidth
+  for (int i = threadIdx.x; i < nl * 8; i += blockDim.x) s_olut[i] = __ldg(&p.out_lut[i >> 3]);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
-  const uint32_t tab = (uint32_t) __cvta_generic_to_shared(s_tab) + ((lane & 15) << 3);
-  const uint32_t olut = (uint32_t) __cvta_generic_to_shared(s_olut) - (0x4B000000u << 2);
+  const uint32_t tab = (uint32_t) __cvta_generic_to_shared(s_tab);  // warp-uniform
+  const uint32_t lane8 = lane << 3;
+  const uint32_t olut = (uint32_t) __cvta_generic_to_shared(s_olut) + ((lane & 7) << 2) - (0x4B000000u << 5);
   const float clamp_lo = p.out_clamp_lo;
   const float fN = (float) (1 << p.out_cells_log2);
   EncK k;
@@ -1245,8 +1249,8 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   unsigned rp = rp0;
 
   auto fetch = [&](uint32_t px, int shift, float &lin, float &cn) {
-    // byte -> table address: (byte << 7); the shift-and-mask is one SHF/LOP pair
-    const uint32_t off = shift >= 7 ? ((px >> (shift - 7)) & 0x7F80u) : ((px << 7) & 0x7F80u);
+    // table offset (byte << 8) | (lane << 3): byte 1 = the pixel's channel byte, byte 0 = lane * 8
+    const uint32_t off = __byte_perm(px, lane8, shift == 16 ? 0x7724 : shift == 8 ? 0x7714 : 0x7704);  // bytes 2,3 = 0 (upper bytes of lane8)
     float2 v;
     asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(tab + off));
     lin = v.x;
@@ -1256,13 +1260,24 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
     float xc = fmaxf(mean, clamp_lo), t;
     asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(t) : "f"(xc), "f"(fN));
     uint32_t e;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((__float_as_uint(t) << 2) + olut));
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((__float_as_uint(t) << 5) + olut));
     return __uint_as_float(__byte_perm(e + __float_as_uint(xc), 0x4B000000u, 0x7543));
   };
 
+  // one-step register prefetch: the loads of step k+1 are issued before the math of step k
+  // (without it 40 % of the warp samples sat on the first use of the loaded pixels)
+  unsigned rpl = rp0;
+  uint4 na = ld_stream_u128(ptr_mad(p.in, oi, 16));
+  uint4 nb = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
   for (unsigned kk = 0; kk < nsteps; kk++) {
-    const uint4 a = ld_stream_u128(ptr_mad(p.in, oi, 16));
-    const uint4 b = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
+    const uint4 a = na, b = nb;
+    rpl += p.d_rp;
+    oi += p.di;
+    if (WRAP && rpl >= rows2) { rpl -= rows2; oi += p.wi; }
+    if (kk + 1 < nsteps) {
+      na = ld_stream_u128(ptr_mad(p.in, oi, 16));
+      nb = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
+    }
     // Walk the four pixel pairs in the order NW, NE (row 0), SW, SE (row 1): pair (0,2) holds the
     // west pixels of blocks A and B, pair (1,3) the east pixels.  Luma is finished per pair; the
     // linear-light sums accumulate in the reference's order ((NW + NE) + SW) + SE (BT709.h:1182-1183).
@@ -1312,8 +1327,8 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
     st_stream_u32((void *) ptr_mad(p.y, oy + p.py4, 4), yw[1]);
     st_stream_u32((void *) ptr_mad(p.c, oc, 4), cw);
     rp += p.d_rp;
-    oi += p.di; oy += p.dy; oc += p.dc;
-    if (WRAP && rp >= rows2) { rp -= rows2; oi += p.wi; oy += p.wy; oc += p.wc; }
+    oy += p.dy; oc += p.dc;
+    if (WRAP && rp >= rows2) { rp -= rows2; oy += p.wy; oc += p.wc; }
   }
 }
 
@@ -1338,7 +1353,7 @@ static int launch_encode_fast(const EncodeArgs &a0, int sm_count, cudaStream_t s
   a.di = d_f * a.si16 + a.d_rp * 2 * a.pi16; a.dy = d_f * a.sy4 + a.d_rp * 2 * a.py4; a.dc = d_f * a.sc4 + a.d_rp * a.pc4;
   a.wi = a.si16 - r2 * 2 * a.pi16; a.wy = a.sy4 - r2 * 2 * a.py4; a.wc = a.sc4 - r2 * a.pc4;
   a.one = 1.0f;
-  const size_t smem = 32768 + ((size_t) (1 << a.out_cells_log2) + 1) * 4;
+  const size_t smem = 65536 + ((size_t) (1 << a.out_cells_log2) + 1) * 32;
   if (wrap)
     k_encode_fast<true><<<grid, 1024, smem, s>>>(a);
   else
@@ -1354,7 +1369,7 @@ int launch_encode(const EncodeArgs &a, int sm_count, void *stream) {
   // fast path: whole 128-pixel tiles, at most 32 tiles per row, offsets that fit 32-bit units
   const unsigned long long in_bytes = (unsigned long long) a.nframes * (a.si > 0 ? a.si : (long long) a.h * a.pi);
   if (vec && a.w % 128 == 0 && a.w <= 4096 && in_bytes < 0xFFFF0000ull * 16 && a.si >= 0 && a.sy >= 0 && a.sc >= 0 &&
-      a.out_cells_log2 <= 13)
+      a.out_cells_log2 <= 12)
     return launch_encode_fast(a, sm_count, s);
   const long long n = (long long) a.nframes * (a.h / 2) * (vec ? a.w / 4 : a.w / 2);
   long long grid = (n + 255) / 256;
@@ -1464,8 +1479,8 @@ static int optin_decode_smem() {
 int kernels_init() {
   int e;
   if ((e = (int) cudaFuncSetAttribute(k_rescale_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 32 + 8193) * 4))) return e;
-  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8193 * 4))) return e;
-  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32768 + 8193 * 4))) return e;
+  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4097 * 32))) return e;
+  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4097 * 32))) return e;
   if ((e = optin_decode_smem<10, 5, false>())) return e;
   if ((e = optin_decode_smem<10, 5, true>())) return e;
   if ((e = optin_decode_smem<12, 3, false>())) return e;
