@@ -939,23 +939,26 @@ struct Lin4 {
   f32x2 rg, ba;  // (R, G), (B, A) in linear light (A is linear already)
 };
 
-__global__ void __launch_bounds__(256) k_rescale_cols(const RescaleArgs p) {
+__global__ void __launch_bounds__(512, 2) k_rescale_cols(const RescaleArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
-  float *s_lin = reinterpret_cast<float *>(s_mem);  // entry b replica r at word b*32 + r
-  uint32_t *s_enc = s_mem + 256 * 32;
+  // sRGB byte -> linear float, one replica per lane; entry stride 256 B so that the table offset
+  // (byte << 8) | (lane << 2) is a single PRMT of the texel word and the lane register
+  float *s_lin = reinterpret_cast<float *>(s_mem);  // entry b replica r at word b*64 + r
+  uint32_t *s_enc = s_mem + 256 * 64;
   const int nenc = (1 << p.enc_cells_log2) + 1;
-  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_lin[i] = __ldg(&p.lin256[i >> 5]);
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_lin[(i >> 5) * 64 + (i & 31)] = __ldg(&p.lin256[i >> 5]);
   for (int i = threadIdx.x; i < nenc; i += blockDim.x) s_enc[i] = __ldg(&p.enc_lut[i]);
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const uint32_t lin_base = (uint32_t) __cvta_generic_to_shared(s_lin) + lane * 4;
+  const uint32_t lin_base = (uint32_t) __cvta_generic_to_shared(s_lin);  // warp-uniform
+  const uint32_t lane4 = lane << 2;
   const uint32_t enc_base = (uint32_t) __cvta_generic_to_shared(s_enc) - (0x4B000000u << 2);
   const float fN = (float) (1 << p.enc_cells_log2);
   const float clamp_lo = p.enc_clamp_lo;
   const f32x2 one = pk(p.one, p.one), inv255_1 = pk(1.0f / 255.0f, 1.0f);
 
   auto lin_of = [&](uint32_t px, int shift) -> float {
-    const uint32_t off = shift >= 7 ? ((px >> (shift - 7)) & 0x7F80u) : ((px << 7) & 0x7F80u);
+    const uint32_t off = __byte_perm(px, lane4, shift == 16 ? 0x7724 : shift == 8 ? 0x7714 : 0x7704);
     float v;
     asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(lin_base + off));
     return v;
@@ -975,13 +978,13 @@ __global__ void __launch_bounds__(256) k_rescale_cols(const RescaleArgs p) {
     return e + __float_as_uint(xc);
   };
 
-  const int tiles_x = (p.ow + 255) / 256, tiles_y = (p.oh + kRescaleTH - 1) / kRescaleTH;
+  const int tiles_x = (p.ow + 511) / 512, tiles_y = (p.oh + kRescaleTH - 1) / kRescaleTH;
   const unsigned tiles_per_frame = tiles_x * tiles_y;
   const unsigned tiles = (unsigned) p.nframes * tiles_per_frame;
   for (unsigned t = blockIdx.x; t < tiles; t += gridDim.x) {
     const unsigned f = t / tiles_per_frame, tr = t - f * tiles_per_frame;
     const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
-    const int ox = tx * 256 + threadIdx.x;
+    const int ox = tx * 512 + threadIdx.x;
     if (ox >= p.ow) continue;
     // horizontal sample position of this column: same float32 steps as oracle_rescale_bgra
     const float sx = __fadd_rn(__fmul_rn(__fadd_rn((float) ox, 0.5f), p.scale_x), -0.5f);
@@ -1063,10 +1066,10 @@ __global__ void __launch_bounds__(256) k_rescale_cols(const RescaleArgs p) {
 
 int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
   if (a.iw <= a.ow && a.ih <= a.oh && a.enc_cells_log2 <= 13) {  // upscale or same size: column walker
-    const size_t smem2 = (256 * 32 + (size_t) (1 << a.enc_cells_log2) + 1) * 4;
-    const long long tiles2 = (long long) a.nframes * ((a.ow + 255) / 256) * ((a.oh + kRescaleTH - 1) / kRescaleTH);
-    long long grid2 = tiles2 < (long long) sm_count * 4 ? tiles2 : (long long) sm_count * 4;
-    k_rescale_cols<<<(unsigned) grid2, 256, smem2, (cudaStream_t) stream>>>(a);
+    const size_t smem2 = (256 * 64 + (size_t) (1 << a.enc_cells_log2) + 1) * 4;
+    const long long tiles2 = (long long) a.nframes * ((a.ow + 511) / 512) * ((a.oh + kRescaleTH - 1) / kRescaleTH);
+    long long grid2 = tiles2 < (long long) sm_count * 2 ? tiles2 : (long long) sm_count * 2;
+    k_rescale_cols<<<(unsigned) grid2, 512, smem2, (cudaStream_t) stream>>>(a);
     return (int) cudaGetLastError();
   }
   const size_t smem = (256 + (size_t) (1 << a.enc_cells_log2) + 1) * 4;
@@ -1478,7 +1481,7 @@ static int optin_decode_smem() {
 // dynamic shared memory for the replicated-LUT decode kernels
 int kernels_init() {
   int e;
-  if ((e = (int) cudaFuncSetAttribute(k_rescale_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 32 + 8193) * 4))) return e;
+  if ((e = (int) cudaFuncSetAttribute(k_rescale_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 64 + 8193) * 4))) return e;
   if ((e = (int) cudaFuncSetAttribute(k_encode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4097 * 32))) return e;
   if ((e = (int) cudaFuncSetAttribute(k_encode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4097 * 32))) return e;
   if ((e = optin_decode_smem<10, 5, false>())) return e;
