@@ -153,6 +153,10 @@ BT709_API int BGRAToBT709Converter_copyBT709ToCoreVideo(MetalRenderContext *mrc,
 BT709_API MBDPixelBuffer *BGRAToBT709Converter_createYCbCrFromBGRA(MetalRenderContext *mrc, const uint32_t *bgraPixels,
                                                                   int width, int height, int isLinear,
                                                                   int asSRGBGamma);
+/* +copyYCBCr:Y:Cb:Cr:dump: (BGRAToBT709Converter.m:688-790): NV12 buffer -> tightly packed planar
+ * Y (w*h), Cb and Cr ((w/2)*(h/2)) as the .y4m writer wants them; the CbCr split runs on the GPU. */
+BT709_API int BGRAToBT709Converter_copyYCBCr(MetalRenderContext *mrc, const MBDPixelBuffer *cvPixelBuffer, uint8_t *Y,
+                                             uint8_t *Cb, uint8_t *Cr);
 /* cvpbu_ycbcr_subsample (CVPixelBufferUtils.h:241-242) */
 BT709_API int cvpbu_ycbcr_subsample(MetalRenderContext *mrc, const uint32_t *inPixelsPtr, int width, int height,
                                     MBDPixelBuffer *dst, BT709Gamma inputGamma, BT709Gamma outputGamma);

@@ -33,7 +33,7 @@ class MBDTexture(ctypes.Structure):
 
 def build(verbose=False):
     """Compile the library in-tree with nvcc for sm_100a (no GPU needed)."""
-    r = subprocess.run(["make", "-C", CSRC], capture_output=True, text=True)
+    r = subprocess.run(["make", "-C", CSRC, "all"], capture_output=True, text=True)
     if verbose or r.returncode != 0:
         print(r.stdout)
         print(r.stderr)
@@ -46,7 +46,7 @@ def _needs_build():
         return True
     t = os.path.getmtime(LIB_PATH)
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".cpp", ".h"))]
-    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("bt709_b200.h", "metal_bt709_decoder.h")]
+    srcs += [os.path.join(_HERE, "..", "include", f) for f in ("bt709_b200.h", "metal_bt709_decoder.h", "y4m_b200.h")]
     return any(os.path.getmtime(s) > t for s in srcs if os.path.exists(s))
 
 
@@ -74,6 +74,14 @@ PROTOTYPES = {
     "bt709_convert_packed444": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),
     "bt709_unconvert_packed444": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),
     "bt709_copy_packed444_to_nv12": (c_int, [c_void_p, c_void_p, PP, PP, c_int, c_int, c_void_p, c_int]),
+    # include/y4m_b200.h
+    "y4m_open_file": (c_void_p, [ctypes.c_char_p]),
+    "y4m_write_header": (c_int, [c_void_p, c_void_p]),
+    "y4m_write_frame": (c_int, [c_void_p, c_void_p]),
+    "y4m_read_header": (c_int, [c_void_p, c_void_p]),
+    "y4m_read_frame": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bt709_cbcr_to_planar": (c_int, [c_void_p, PP, PP, PP, c_int, c_int, c_int, c_void_p, c_int]),
+    "bt709_planar_to_cbcr": (c_int, [c_void_p, PP, PP, PP, c_int, c_int, c_int, c_void_p, c_int]),
     # include/metal_bt709_decoder.h
     "MetalRenderContext_new": (c_void_p, [c_int]),
     "MetalRenderContext_release": (None, [c_void_p]),
@@ -102,6 +110,7 @@ PROTOTYPES = {
     "BGRAToBT709Converter_unconvert": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
     "BGRAToBT709Converter_copyBT709ToCoreVideo": (c_int, [c_void_p, c_void_p, PPB]),
     "BGRAToBT709Converter_createYCbCrFromBGRA": (PPB, [c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
+    "BGRAToBT709Converter_copyYCBCr": (c_int, [c_void_p, PPB, c_void_p, c_void_p, c_void_p]),
     "cvpbu_ycbcr_subsample": (c_int, [c_void_p, c_void_p, c_int, c_int, PPB, c_int, c_int]),
     "AAPLRenderer_new": (c_void_p, [c_void_p, c_int, c_int]),
     "AAPLRenderer_release": (None, [c_void_p]),

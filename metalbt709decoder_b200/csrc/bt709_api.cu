@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../include/bt709_b200.h"
+#include "../../include/y4m_b200.h"
 #include "bt709_kernels.cuh"
 #include "bt709_tables.h"
 
@@ -330,6 +331,34 @@ int bt709_copy_packed444_to_nv12(const bt709_ctx *ctx, const uint32_t *in, const
   a.in = in; a.y = (uint8_t *) y->ptr; a.py = (long long) y->pitch; a.c = (uint8_t *) cbcr->ptr;
   a.pc = (long long) cbcr->pitch; a.w = w; a.h = h;
   return finish(ctx, launch_copy_packed(a, stream), stream, wait);
+}
+
+static int cbcr_planar(const bt709_ctx *ctx, const bt709_plane *cbcr, const bt709_plane *u, const bt709_plane *v, int cw,
+                       int ch, int nframes, void *stream, int wait, bool split) {
+  if (!ctx || !plane_ok(cbcr) || !plane_ok(u) || !plane_ok(v)) return BT709_E_NULL;
+  if (cw <= 0 || ch <= 0 || nframes <= 0) return BT709_E_DIMS;
+  int rc;
+  if ((rc = check_plane(cbcr, (size_t) cw * 2, ch, nframes))) return rc;
+  if ((rc = check_plane(u, cw, ch, nframes))) return rc;
+  if ((rc = check_plane(v, cw, ch, nframes))) return rc;
+  DeviceGuard guard(ctx->device);
+  if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
+  PlanarArgs a{};
+  a.c = (uint8_t *) cbcr->ptr; a.pc = (long long) cbcr->pitch; a.sc = (long long) cbcr->frame_stride;
+  a.u = (uint8_t *) u->ptr; a.pu = (long long) u->pitch; a.su = (long long) u->frame_stride;
+  a.v = (uint8_t *) v->ptr; a.pv = (long long) v->pitch; a.sv = (long long) v->frame_stride;
+  a.cw = cw; a.ch = ch; a.nframes = nframes;
+  return finish(ctx, launch_cbcr_planar(a, split, stream), stream, wait);
+}
+
+int bt709_cbcr_to_planar(const bt709_ctx *ctx, const bt709_plane *cbcr, const bt709_plane *u, const bt709_plane *v,
+                         int cw, int ch, int nframes, void *stream, int wait) {
+  return cbcr_planar(ctx, cbcr, u, v, cw, ch, nframes, stream, wait, true);
+}
+
+int bt709_planar_to_cbcr(const bt709_ctx *ctx, const bt709_plane *u, const bt709_plane *v, const bt709_plane *cbcr,
+                         int cw, int ch, int nframes, void *stream, int wait) {
+  return cbcr_planar(ctx, cbcr, u, v, cw, ch, nframes, stream, wait, false);
 }
 
 }  // extern "C"

@@ -6,6 +6,8 @@
 // upload, compute and read-back.  No arithmetic happens on the host.
 #include "bt709_host.h"
 
+#include "../../include/y4m_b200.h"
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -404,6 +406,28 @@ int BGRAToBT709Converter_copyBT709ToCoreVideo(MetalRenderContext *mrc, const uin
     ok = bt709_copy_packed444_to_nv12(mrc->ctx, (const uint32_t *) s->in.p, &y, &c, w, h, st, 0) == BT709_OK;
     ok = ok && download2d(pb->y, pb->yBytesPerRow, s->y.p, py, w, h, st);
     ok = ok && download2d(pb->cbcr, pb->cbcrBytesPerRow, s->c.p, pc, cw, ch, st);
+  }
+  return finish(s, st, ok, 1) ? 1 : 0;
+}
+
+int BGRAToBT709Converter_copyYCBCr(MetalRenderContext *mrc, const MBDPixelBuffer *pb, uint8_t *Y, uint8_t *Cb, uint8_t *Cr) {
+  if (!mrc || !pb || !pb->y || !pb->cbcr || !Y || !Cb || !Cr) return 0;
+  const int w = pb->width, h = pb->height;
+  if ((w % 2) != 0 || (h % 2) != 0) return 0;  // BGRAToBT709Converter.m:697-698
+  if (!MetalRenderContext_setupMetal(mrc)) return 0;
+  for (int row = 0; row < h; row++) memcpy(Y + (size_t) row * w, pb->y + (size_t) row * pb->yBytesPerRow, w);
+  Guard g(mrc->device);
+  cudaStream_t st;
+  Slot *s = acquire(mrc, nullptr, &st);
+  const int cw = w / 2, ch = h / 2;
+  const size_t pc = align_up((size_t) w, 256), pu = align_up((size_t) cw, 256);
+  bool ok = s->c.ensure(pc * ch) && s->y.ensure(2 * pu * ch);
+  ok = ok && upload2d(s->c.p, pc, pb->cbcr, pb->cbcrBytesPerRow, (size_t) w, ch, st);
+  if (ok) {
+    bt709_plane c = {s->c.p, pc, pc * ch}, u = {s->y.p, pu, pu * ch}, v = {(uint8_t *) s->y.p + pu * ch, pu, pu * ch};
+    ok = bt709_cbcr_to_planar(mrc->ctx, &c, &u, &v, cw, ch, 1, st, 0) == BT709_OK;
+    ok = ok && download2d(Cb, cw, u.ptr, pu, cw, ch, st);
+    ok = ok && download2d(Cr, cw, v.ptr, pu, cw, ch, st);
   }
   return finish(s, st, ok, 1) ? 1 : 0;
 }

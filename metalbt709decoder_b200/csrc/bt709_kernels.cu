@@ -1437,6 +1437,35 @@ __global__ void __launch_bounds__(256) k_copy_packed(const CopyPackedArgs p) {
   }
 }
 
+// ======================================================================= NV12 <-> planar chroma
+// +copyYCBCr: (BGRAToBT709Converter.m:688-790) splits CbCr pairs into U and V planes for the .y4m
+// writer; the inverse feeds .y4m frames to the decoder.  Pure byte shuffles, 2 B/sample each way.
+template <bool SPLIT>
+__global__ void __launch_bounds__(256) k_cbcr_planar(const PlanarArgs p) {
+  const long long n = (long long) p.nframes * p.ch * p.cw;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+    const int x = (int) (i % p.cw);
+    const long long r = i / p.cw;
+    const int y = (int) (r % p.ch);
+    const long long f = r / p.ch;
+    uint8_t *c = p.c + f * p.sc + (long long) y * p.pc + 2 * x;
+    uint8_t *u = p.u + f * p.su + (long long) y * p.pu + x;
+    uint8_t *v = p.v + f * p.sv + (long long) y * p.pv + x;
+    if (SPLIT) { *u = c[0]; *v = c[1]; } else { c[0] = *u; c[1] = *v; }
+  }
+}
+
+int launch_cbcr_planar(const PlanarArgs &a, bool split, void *stream) {
+  const long long n = (long long) a.nframes * a.ch * a.cw;
+  long long g = (n + 255) / 256;
+  g = g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g);
+  if (split)
+    k_cbcr_planar<true><<<(unsigned) g, 256, 0, (cudaStream_t) stream>>>(a);
+  else
+    k_cbcr_planar<false><<<(unsigned) g, 256, 0, (cudaStream_t) stream>>>(a);
+  return (int) cudaGetLastError();
+}
+
 static unsigned grid_1d(long long n) {
   long long g = (n + 255) / 256;
   return (unsigned) (g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g));

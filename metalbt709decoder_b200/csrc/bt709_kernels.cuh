@@ -79,6 +79,12 @@ struct CopyPackedArgs {
   int w, h;
 };
 
+struct PlanarArgs {
+  uint8_t *c, *u, *v;
+  long long pc, pu, pv, sc, su, sv;
+  int cw, ch, nframes;
+};
+
 // launchers (bt709_kernels.cu).  Each returns the cudaError_t of the launch.
 int launch_decode(const DecodeArgs &a, int sm_count, void *stream);
 int launch_rescale(const RescaleArgs &a, int sm_count, void *stream);
@@ -86,6 +92,7 @@ int launch_encode(const EncodeArgs &a, int sm_count, void *stream);
 int launch_convert444(const Packed444Args &a, void *stream);
 int launch_unconvert444(const Packed444Args &a, void *stream);
 int launch_copy_packed(const CopyPackedArgs &a, void *stream);
+int launch_cbcr_planar(const PlanarArgs &a, bool split, void *stream);
 // one-time per-device kernel attribute setup (dynamic shared memory opt-in)
 int kernels_init();
 

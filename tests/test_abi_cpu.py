@@ -20,7 +20,7 @@ def _declared(header):
 
 def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIB_PATH) if os.path.exists(_lib.LIB_PATH) else _lib.lib()
-    names = _declared("bt709_b200.h") + _declared("metal_bt709_decoder.h")
+    names = _declared("bt709_b200.h") + _declared("metal_bt709_decoder.h") + _declared("y4m_b200.h")
     assert len(names) >= 40
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/ but not exported"
