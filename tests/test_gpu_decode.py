@@ -190,3 +190,58 @@ print("bulk ok")
     env = dict(os.environ, BT709_BULK="1")
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "bulk ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_padded_frame_strides_take_the_wrap_path():
+    """frames separated by padding (frame_stride > rows * pitch): the kernels step across frame seams"""
+    from _gpu import ctx
+    w, h, F = 256, 36, 7
+    ys, cs, wants = [], [], []
+    ybig = torch.zeros((F, h + 3, w + 64), dtype=torch.uint8, device="cuda")
+    cbig = torch.zeros((F, h // 2 + 5, w + 128), dtype=torch.uint8, device="cuda")
+    obig = torch.zeros((F, h + 2, w + 16, 4), dtype=torch.uint8, device="cuda")
+    for f in range(F):
+        y, c = frame_random(w, h, seed=40 + f)
+        ybig[f, :h, :w] = torch.from_numpy(y).cuda()
+        cbig[f, :h // 2, :w] = torch.from_numpy(c).cuda()
+        wants.append(ORA.decode_nv12(3, y, c))
+    for env_gamma in (3, 2):
+        obig.zero_()
+        ctx().decode_nv12(env_gamma, ybig[:, :h, :w], cbig[:, :h // 2, :w], obig[:, :h, :w], w=w, h=h, wait=True)
+        got = obig[:, :h, :w].cpu().numpy()
+        if env_gamma == 3:
+            _check(got, np.stack(wants), "strided batch")
+        assert int(obig[:, h:].max()) == 0 and int(obig[:, :, w:].max()) == 0  # padding untouched
+
+
+def test_offsets_beyond_32_bits_are_split_across_launches():
+    """a batch whose planes span more than 4 GiB (sparse frame strides): the 32-bit unit offsets of the
+    fast kernels cannot address it in one launch, so the launcher splits it"""
+    from _gpu import ctx
+    from metalbt709decoder_b200._lib import Plane
+    import ctypes
+    w, h, F = 256, 8, 3
+    stride_y = (5 << 30) // 2 + 4096          # 2.5 GiB between Y frames
+    stride_o = (36 << 30) + 65536             # 36 GiB between BGRA frames: > 2^32 * 16 B in two frames
+    free, _ = torch.cuda.mem_get_info()
+    need = stride_y * (F - 1) + stride_o * (F - 1) + (1 << 30)
+    if free < need:
+        pytest.skip("not enough free device memory")
+    ybuf = torch.empty(stride_y * (F - 1) + w * h, dtype=torch.uint8, device="cuda")
+    obuf = torch.empty(stride_o * (F - 1) + w * h * 4, dtype=torch.uint8, device="cuda")
+    cbuf = torch.empty((F, h // 2, w), dtype=torch.uint8, device="cuda")
+    wants = []
+    for f in range(F):
+        y, c = frame_random(w, h, seed=60 + f)
+        ybuf[f * stride_y:f * stride_y + w * h] = torch.from_numpy(y).cuda().reshape(-1)
+        cbuf[f] = torch.from_numpy(c).cuda()
+        wants.append(ORA.decode_nv12(0, y, c))
+    C = ctx()
+    py = Plane(ybuf.data_ptr(), w, stride_y)
+    pc = Plane(cbuf.data_ptr(), w, (h // 2) * w)
+    po = Plane(obuf.data_ptr(), w * 4, stride_o)
+    rc = C.decode_nv12_raw(0, ctypes.byref(py), ctypes.byref(pc), None, ctypes.byref(po), w, h, F, wait=True)
+    assert rc == 0
+    for f in range(F):
+        got = obuf[f * stride_o:f * stride_o + w * h * 4].view(h, w, 4).cpu().numpy()
+        _check(got, wants[f], f"frame {f} of a >4 GiB batch")
