@@ -1,0 +1,772 @@
+// bt709_decode.cu — pass 1: video-range BT.709 NV12 -> sRGB BGRA8 (sm_100a kernels + launcher).
+//
+// Replaces the decode kernels/fragments of AAPLShaders.metal:180-438 and the dispatch of
+// MetalBT709Decoder.m:497-610.  All arithmetic that feeds a quantiser is done with explicitly
+// rounded float32 operations (never contracted to FMA) in the order the reference's CPU code uses
+// (BT709.h:389-397, 424-426, 494-500), and every transfer curve is an exact table lookup
+// (bt709_tables.h), so results are bit-identical to the reference's CPU path, not merely +-1 LSB.
+//
+// No tensor cores: the path is a per-pixel map with 5.5 B/pixel of HBM traffic and no contraction.
+// What matters is (a) 16-byte coalesced stores and wide enough load requests with enough bytes in
+// flight per SM, (b) keeping the per-pixel instruction count under the issue budget (about 37
+// warp-instructions per 32 pixels at 80 % of the HBM roofline), (c) keeping the three curve lookups
+// per pixel off the MUFU pipe and free of shared-memory bank conflicts (per-lane replicated LUT).
+//
+// Kernels (all share decode_row / tile_compute_store):
+//   k_decode_ring     default: per-warp cp.async shared-memory ring for the inputs
+//   k_decode_fast     fallback: per-thread LDG with register prefetch (any 4-byte aligned planes)
+//   k_decode_bulk     opt-in (BT709_BULK=1): cp.async.bulk row copies + mbarriers; measured slower
+//   k_decode_generic  any size, pitch and alignment; one thread per 2x2 block
+//
+// Tile shape of the fast kernels: a warp owns 128 pixels x 2 rows (one chroma row); lane l handles
+// pixels [4l, 4l+4) of both rows, so every warp-level access is contiguous:
+//   Y     2 rows x 128 B,   CbCr  1 x 128 B (read once, used for both rows: nearest 4:2:0 upsample),
+//   BGRA  2 rows x STG.128 = 512 B per instruction.
+// A pair of packed floats always holds the same pixel position of chroma pair A (pixels 0,1) and
+// chroma pair B (pixels 2,3), so chroma products pair up naturally with the luma terms.
+#include "bt709_device.cuh"
+
+namespace bt709 {
+
+// loop-invariant packed constants {k, k}
+struct DecodeK2 {
+  f32x2 kY, kC, inv255, ys, g_cb, b_cb, r_cr, g_cr, fN, magic, one;
+};
+// two LUT lookups at once: clamp (scalar), index (packed FFMA2.RZ), two LDS, two adds.
+// returns the two sums whose byte 3 is the 8-bit code
+template <int CL2, int RL2>
+__device__ __forceinline__ void lut2(float xa, float xb, float clamp_lo, const DecodeK2 &k, uint32_t sbase,
+                                     uint32_t &sa, uint32_t &sb) {
+  float ca = fmaxf(xa, clamp_lo), cb = fmaxf(xb, clamp_lo);
+  uint32_t ta, tb;
+  upku(fma2_rz(pk(ca, cb), k.fN, k.magic), ta, tb);
+  uint32_t ea, eb;
+  asm("ld.shared.u32 %0, [%1];" : "=r"(ea) : "r"((ta << (2 + RL2)) + sbase));
+  asm("ld.shared.u32 %0, [%1];" : "=r"(eb) : "r"((tb << (2 + RL2)) + sbase));
+  sa = ea + __float_as_uint(ca);
+  sb = eb + __float_as_uint(cb);
+}
+
+template <int CL2, int RL2, bool ALPHA>
+__device__ __forceinline__ uint4 decode_row(uint32_t yw, uint32_t aw, f32x2 cb_g, f32x2 cb_b, f32x2 cr_r, f32x2 cr_g,
+                                            const DecodeK2 &k, float clamp_lo, uint32_t sbase) {
+  // luma terms, BT709.h:494 then :424 — pairs (px0, px2) and (px1, px3)
+  f32x2 y02 = mul2(mul2(add2(pku(magic_byte<0>(yw), magic_byte<2>(yw)), k.kY), k.inv255), k.ys);
+  f32x2 y13 = mul2(mul2(add2(pku(magic_byte<1>(yw), magic_byte<3>(yw)), k.kY), k.inv255), k.ys);
+  // (Y + Cb) first, then + Cr (BT709.h:425).  ptxas contracts a packed mul.rn.f32x2 feeding an
+  // add.rn.f32x2 into one FFMA2 (a single rounding: not bit-exact), so the packed add is written as
+  // fma(y, one, cb_g) with `one` = 1.0f read from the kernel arguments: y*1 is exact, the sum is
+  // rounded once exactly like an add, and neither multiply can be folded into it.
+  f32x2 g02 = fma2_rn(y02, k.one, cb_g), g13 = fma2_rn(y13, k.one, cb_g);
+  float y0, y1, y2, y3, g0, g1, g2, g3, crA, crB, cgA, cgB, cbA, cbB;
+  upk(y02, y0, y2); upk(y13, y1, y3);
+  upk(g02, g0, g2); upk(g13, g1, g3);
+  upk(cr_r, crA, crB); upk(cr_g, cgA, cgB); upk(cb_b, cbA, cbB);
+  uint32_t r0, r1, r2, r3, gg0, gg1, gg2, gg3, b0, b1, b2, b3;
+  lut2<CL2, RL2>(add_sat(y0, crA), add_sat(y2, crB), clamp_lo, k, sbase, r0, r2);
+  lut2<CL2, RL2>(add_sat(y1, crA), add_sat(y3, crB), clamp_lo, k, sbase, r1, r3);
+  lut2<CL2, RL2>(add_sat(g0, cgA), add_sat(g2, cgB), clamp_lo, k, sbase, gg0, gg2);
+  lut2<CL2, RL2>(add_sat(g1, cgA), add_sat(g3, cgB), clamp_lo, k, sbase, gg1, gg3);
+  lut2<CL2, RL2>(add_sat(y0, cbA), add_sat(y2, cbB), clamp_lo, k, sbase, b0, b2);
+  lut2<CL2, RL2>(add_sat(y1, cbA), add_sat(y3, cbB), clamp_lo, k, sbase, b1, b3);
+  uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+  if (ALPHA) {
+    // AAPLShaders.metal:249-271 via the CPU twin BT709.h:466-513 with neutral chroma
+    f32x2 a02 = mul2(mul2(add2(pku(magic_byte<0>(aw), magic_byte<2>(aw)), k.kY), k.inv255), k.ys);
+    f32x2 a13 = mul2(mul2(add2(pku(magic_byte<1>(aw), magic_byte<3>(aw)), k.kY), k.inv255), k.ys);
+    float f0, f1, f2, f3;
+    upk(a02, f0, f2); upk(a13, f1, f3);
+    a0 = (uint32_t) round_pos(__fmul_rn(add_sat(f0, 0.0f), 255.0f));
+    a1 = (uint32_t) round_pos(__fmul_rn(add_sat(f1, 0.0f), 255.0f));
+    a2 = (uint32_t) round_pos(__fmul_rn(add_sat(f2, 0.0f), 255.0f));
+    a3 = (uint32_t) round_pos(__fmul_rn(add_sat(f3, 0.0f), 255.0f));
+  }
+  auto pack = [](uint32_t sb, uint32_t sg, uint32_t sr, uint32_t a) -> uint32_t {
+    uint32_t bg = __byte_perm(sb, sg, 0x0073);  // byte0 = B code, byte1 = G code
+    if (ALPHA) return __byte_perm(bg, __byte_perm(sr, a, 0x0043), 0x5410);
+    return __byte_perm(bg, sr, 0x7710) | 0xFF000000u;  // A = 255 (AAPLShaders.metal:243)
+  };
+  return make_uint4(pack(b0, gg0, r0, a0), pack(b1, gg1, r1, a1), pack(b2, gg2, r2, a2), pack(b3, gg3, r3, a3));
+}
+
+// Work layout.  A warp owns a 128-pixel x 2-row tile (lane l: pixels [4l, 4l+4) of both rows).
+// The warps of the CTA sit side by side: they cover `rps` complete row pairs per step
+// (rps = warps / tiles per row), so a CTA touches 2*rps whole contiguous rows of Y, rps rows of
+// CbCr and 2*rps rows of BGRA at a time, and consecutive CTAs take consecutive bands.  That keeps
+// DRAM pages hot (a warp streaming its own row did not: 4736 independent row streams measured
+// 51 % long-scoreboard stalls at 4.2 TB/s).  Each warp's (tile, row-in-band) is fixed for the whole
+// kernel; per step only (frame, row pair) advance, by a constant with a carry, and every address
+// is two IMAD.WIDE away.  The loads of the next step are issued before the current step is
+// computed; the loop is unrolled twice so the two load buffers ping-pong without moves.
+// FULL = (w % 128 == 0 && h % 2 == 0): no per-lane or per-row predicates anywhere.
+template <bool ALPHA>
+struct TileLoad {
+  uint32_t y0, y1, c, a0, a1;
+};
+
+// Addressing.  Every plane is addressed as base + 32-bit offset in load/store units (4 bytes
+// for Y / CbCr / alpha, 16 bytes for BGRA), so an address is a single IMAD.WIDE.U32 and stepping
+// to the next (frame, row pair) is one 32-bit add per plane plus a predicated add on a frame
+// wrap.  The launcher splits batches whose offsets would not fit in 32 bits.
+template <bool ALPHA, bool FULL>
+__device__ __forceinline__ void tile_load(const DecodeArgs &p, unsigned oy, unsigned oc, unsigned oa, unsigned rp,
+                                          bool valid, TileLoad<ALPHA> &t) {
+  const bool has_row1 = FULL || rp * 2 + 1 < (unsigned) p.h;
+  if (!FULL) t.y0 = t.y1 = t.c = t.a0 = t.a1 = 0;
+  if (FULL || valid) {
+    t.y0 = ld_stream_u32(ptr_mad(p.y, oy, 4));
+    t.c = ld_stream_u32(ptr_mad(p.c, oc, 4));
+    if (has_row1) t.y1 = ld_stream_u32(ptr_mad(p.y, oy + p.py4, 4));
+    if (ALPHA) {
+      t.a0 = ld_stream_u32(ptr_mad(p.a, oa, 4));
+      if (has_row1) t.a1 = ld_stream_u32(ptr_mad(p.a, oa + p.pa4, 4));
+    }
+  }
+}
+
+template <int CL2, int RL2, bool ALPHA, bool FULL>
+__device__ __forceinline__ void tile_compute_store(const DecodeArgs &p, unsigned oo, unsigned rp, bool valid,
+                                                   const TileLoad<ALPHA> &t, const DecodeK2 &k, float clamp_lo,
+                                                   uint32_t sbase) {
+  if (!FULL && !valid) return;
+  const bool has_row1 = FULL || rp * 2 + 1 < (unsigned) p.h;
+  // chroma pairs A (bytes 0,1) and B (bytes 2,3): BT709.h:499-500 then the matrix columns
+  f32x2 cbn = mul2(add2(pku(magic_byte<0>(t.c), magic_byte<2>(t.c)), k.kC), k.inv255);
+  f32x2 crn = mul2(add2(pku(magic_byte<1>(t.c), magic_byte<3>(t.c)), k.kC), k.inv255);
+  f32x2 cb_g = mul2(cbn, k.g_cb), cb_b = mul2(cbn, k.b_cb);
+  f32x2 cr_r = mul2(crn, k.r_cr), cr_g = mul2(crn, k.g_cr);
+  st_stream_u128((uint8_t *) ptr_mad(p.out, oo, 16),
+                 decode_row<CL2, RL2, ALPHA>(t.y0, t.a0, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+  if (has_row1)
+    st_stream_u128((uint8_t *) ptr_mad(p.out, oo + p.po16, 16),
+                   decode_row<CL2, RL2, ALPHA>(t.y1, t.a1, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+}
+
+// WRAP = false: the batch is one contiguous tall image (frame stride == rows * pitch for every
+// plane), so stepping never crosses a frame seam and the carry logic disappears.
+template <int CL2, int RL2, bool ALPHA, bool FULL, bool WRAP, int PD, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) {
+  extern __shared__ __align__(128) uint32_t s_lut[];
+  constexpr int N = 1 << CL2, R = 1 << RL2;
+  for (int i = threadIdx.x; i < (N + 1) * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(s_lut) + ((lane & (R - 1)) << 2) -
+                         (0x4B000000u << (2 + RL2));
+  const float clamp_lo = p.clamp_lo;
+  DecodeK2 k;
+  k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
+  k.kC = pk(-(8388608.0f + 128.0f), -(8388608.0f + 128.0f));
+  k.inv255 = pk(p.m.inv255, p.m.inv255);
+  k.ys = pk(p.m.ys, p.m.ys);
+  k.g_cb = pk(p.m.g_cb, p.m.g_cb);
+  k.b_cb = pk(p.m.b_cb, p.m.b_cb);
+  k.r_cr = pk(p.m.r_cr, p.m.r_cr);
+  k.g_cr = pk(p.m.g_cr, p.m.g_cr);
+  k.fN = pk((float) N, (float) N);
+  k.magic = pk(8388608.0f, 8388608.0f);
+  k.one = pk(p.one, p.one);
+
+  // this warp's place in the CTA's band: fixed for the whole kernel
+  const unsigned r_local = warp / p.tiles_per_row;
+  if (r_local >= (unsigned) p.rps) return;  // spare warps when the warp count is not a multiple of the tiles per row
+  const unsigned tile0 = warp - r_local * p.tiles_per_row;
+  const unsigned rows2 = p.rows2;
+  const unsigned total_rp = (unsigned) p.nframes * rows2;
+  const unsigned rpg0 = blockIdx.x * p.rps + r_local;
+  if (rpg0 >= total_rp) return;
+  const unsigned f0 = rpg0 / rows2, rp0 = rpg0 - f0 * rows2;
+  const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;  // >= 1
+
+  for (unsigned tile = tile0; tile < (unsigned) p.tiles_per_row; tile += p.tile_stride) {
+    const unsigned col4 = tile * 32 + lane;  // column in 4-pixel units
+    const bool valid = FULL || (int) (col4 * 4) < p.w;
+    // Two offset streams: the load stream runs PD steps ahead of the store stream.  Measured
+    // (tools/probes/gran_bw.cu): with 1024 threads per SM the HBM pipe needs >= 24 B of loads in
+    // flight per thread to reach 6 TB/s at this byte mix; 12 B (one step ahead) gave 4.4 TB/s.
+    unsigned oy = f0 * p.sy4 + rp0 * 2 * p.py4 + col4;
+    unsigned oc = f0 * p.sc4 + rp0 * p.pc4 + col4;
+    unsigned oa = ALPHA ? f0 * p.sa4 + rp0 * 2 * p.pa4 + col4 : 0;
+    unsigned oo = f0 * p.so16 + rp0 * 2 * p.po16 + col4;
+    unsigned rpl = rp0, rps_ = rp0;  // row pair of the next load / of the next store
+    constexpr int NB = PD + 1;
+    TileLoad<ALPHA> buf[NB];
+    auto advance_load = [&]() {
+      rpl += p.d_rp;
+      oy += p.dy; oc += p.dc;
+      if (ALPHA) oa += p.da;
+      if (WRAP && rpl >= rows2) { rpl -= rows2; oy += p.wy; oc += p.wc; if (ALPHA) oa += p.wa; }
+    };
+#pragma unroll
+    for (int j = 0; j < PD; j++) {
+      if ((unsigned) j < nsteps) {
+        tile_load<ALPHA, FULL>(p, oy, oc, oa, rpl, valid, buf[j]);
+        advance_load();
+      }
+    }
+    unsigned kk = 0;
+    while (true) {
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        if (kk + PD < nsteps) {
+          tile_load<ALPHA, FULL>(p, oy, oc, oa, rpl, valid, buf[(j + PD) % NB]);
+          advance_load();
+        }
+        tile_compute_store<CL2, RL2, ALPHA, FULL>(p, oo, rps_, valid, buf[j], k, clamp_lo, sbase);
+        rps_ += p.d_rp;
+        oo += p.dout;
+        if (WRAP && rps_ >= rows2) { rps_ -= rows2; oo += p.wout; }
+        if (++kk >= nsteps) goto tile_done;
+      }
+    }
+  tile_done:;
+  }
+}
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+// ================================================================= decode, cp.async warp ring
+// Same arithmetic and CTA-band layout as k_decode_fast, but each warp stages its own inputs through
+// a private shared-memory ring: per step ONE cp.async instruction (16 bytes per lane; lanes 0-7
+// fetch the 128 B of Y row 0, lanes 8-15 Y row 1, lanes 16-23 the CbCr row) replaces three
+// LDG.32 and their address arithmetic, and the bytes in flight live in shared memory instead of
+// registers (D - 1 steps ahead).  Needs FULL geometry and 16-byte aligned Y / CbCr planes.
+template <int CL2, int RL2, bool ALPHA, bool WRAP, int D, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) {
+  extern __shared__ __align__(128) uint32_t s_lut[];
+  constexpr int N = 1 << CL2, R = 1 << RL2;
+  constexpr uint32_t kLutBytes = (uint32_t) (N + 1) * R * 4;
+  constexpr uint32_t kStage = ALPHA ? 640 : 384;  // Y0 | Y1 | CbCr (| A0 | A1), 128 B each
+  for (int i = threadIdx.x; i < (N + 1) * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_lut);
+  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - (0x4B000000u << (2 + RL2));
+  const uint32_t ring = smem0 + kLutBytes + warp * (D * kStage);
+  const float clamp_lo = p.clamp_lo;
+  DecodeK2 k;
+  k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
+  k.kC = pk(-(8388608.0f + 128.0f), -(8388608.0f + 128.0f));
+  k.inv255 = pk(p.m.inv255, p.m.inv255);
+  k.ys = pk(p.m.ys, p.m.ys);
+  k.g_cb = pk(p.m.g_cb, p.m.g_cb);
+  k.b_cb = pk(p.m.b_cb, p.m.b_cb);
+  k.r_cr = pk(p.m.r_cr, p.m.r_cr);
+  k.g_cr = pk(p.m.g_cr, p.m.g_cr);
+  k.fN = pk((float) N, (float) N);
+  k.magic = pk(8388608.0f, 8388608.0f);
+  k.one = pk(p.one, p.one);
+
+  const unsigned r_local = warp / p.tiles_per_row;
+  if (r_local >= (unsigned) p.rps) return;
+  const unsigned tile = warp - r_local * p.tiles_per_row;
+  const unsigned rows2 = p.rows2;
+  const unsigned total_rp = (unsigned) p.nframes * rows2;
+  const unsigned rpg0 = blockIdx.x * p.rps + r_local;
+  if (rpg0 >= total_rp) return;
+  const unsigned f0 = rpg0 / rows2, rp0 = rpg0 - f0 * rows2;
+  const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;
+
+  // ---- copy role of this lane: which plane row it fetches, as base + 32-bit offset in 4-byte units
+  const int role = lane >> 3, sub = lane & 7;  // 0: Y row 0, 1: Y row 1, 2: CbCr, 3: idle (alpha: second pass)
+  const uint8_t *cbase = role < 2 ? p.y : p.c;
+  unsigned coff = role < 2 ? f0 * p.sy4 + (rp0 * 2 + role) * p.py4 : f0 * p.sc4 + rp0 * p.pc4;
+  coff += tile * 32 + sub * 4;
+  const unsigned cinc = role < 2 ? p.dy : p.dc, cwrap = role < 2 ? p.wy : p.wc;
+  const uint32_t cdst = role * 128 + sub * 16;
+  // alpha rows (ALPHA only): lanes 0-7 row 0, lanes 8-15 row 1, via a second cp.async
+  unsigned aoff = ALPHA ? f0 * p.sa4 + (rp0 * 2 + (role & 1)) * p.pa4 + tile * 32 + sub * 4 : 0;
+  const uint32_t adst = 384 + (role & 1) * 128 + sub * 16;
+  unsigned rpl = rp0;
+
+  auto issue = [&](uint32_t slot) {
+    if (role < 3)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + slot * kStage + cdst),
+                   "l"(ptr_mad(cbase, coff, 4))
+                   : "memory");
+    if (ALPHA && role < 2)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring + slot * kStage + adst),
+                   "l"(ptr_mad(p.a, aoff, 4))
+                   : "memory");
+    // step this lane's source to the warp's row pair in the CTA's next band
+    rpl += p.d_rp;
+    coff += cinc;
+    if (ALPHA) aoff += p.da;
+    if (WRAP && rpl >= rows2) { rpl -= rows2; coff += cwrap; if (ALPHA) aoff += p.wa; }
+  };
+
+  const unsigned col4 = tile * 32 + lane;
+  unsigned oo = f0 * p.so16 + rp0 * 2 * p.po16 + col4;
+  unsigned rps_ = rp0;
+#pragma unroll
+  for (int j = 0; j < D - 1; j++) {
+    if ((unsigned) j < nsteps) issue(j);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  uint32_t slot = 0, fill = D - 1;
+  for (unsigned kk = 0; kk < nsteps; kk++) {
+    if (kk + D - 1 < nsteps) issue(fill);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+    __syncwarp();
+    const uint32_t st = ring + slot * kStage + lane * 4;
+    TileLoad<ALPHA> t;
+    t.y0 = lds_u32(st);
+    t.y1 = lds_u32(st + 128);
+    t.c = lds_u32(st + 256);
+    if (ALPHA) {
+      t.a0 = lds_u32(st + 384);
+      t.a1 = lds_u32(st + 512);
+    }
+    __syncwarp();  // every lane has its words before this slot is refilled
+    tile_compute_store<CL2, RL2, ALPHA, true>(p, oo, rps_, true, t, k, clamp_lo, sbase);
+    rps_ += p.d_rp;
+    oo += p.dout;
+    if (WRAP && rps_ >= rows2) { rps_ -= rows2; oo += p.wout; }
+    slot = slot + 1 == D ? 0 : slot + 1;
+    fill = fill + 1 == D ? 0 : fill + 1;
+  }
+}
+
+// ===================================================================== decode, bulk-staged
+// Same arithmetic and the same CTA-band work layout as k_decode_fast, but the input planes reach
+// the SM through the bulk async-copy engine (cp.async.bulk -> UBLKCP, the 1-D TMA path) into a
+// shared-memory ring instead of through per-thread LDG into registers.
+//
+// Why: with per-thread loads the bytes in flight per SM are bounded by registers
+// (32 warps x 3 x 128 B = 12 KB), and the measured throughput was the same 4.46 TB/s with the
+// arithmetic compiled out - a latency (Little's law) bound, not an issue bound.  A ring of up to 8
+// stages x 11.5 KB keeps ~90 KB of reads in flight per SM, costs no registers, and removes every
+// load address computation from the consumer warps.
+//
+//   stage  = one CTA band: 2*rps rows of Y and rps rows of CbCr (and 2*rps rows of alpha),
+//            each row one bulk copy of w bytes, issued by lane 0 of warp j for row j
+//   full[s]   mbarrier, count = rows per stage, completes when all bytes of the stage have landed
+//   empty[s]  mbarrier, count = consumer warps, completes when every warp has read its words
+// Requires w % 128 == 0, h even, 16-byte aligned planes and pitches (else k_decode_fast).
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+template <int CL2, int RL2, bool ALPHA, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_decode_bulk(const DecodeArgs p) {
+  extern __shared__ __align__(128) uint32_t s_lut[];
+  constexpr int N = 1 << CL2, R = 1 << RL2;
+  constexpr uint32_t kLutBytes = (uint32_t) (N + 1) * R * 4;
+  for (int i = threadIdx.x; i < (N + 1) * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+
+  const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_lut);
+  const uint32_t ring0 = smem0 + kLutBytes;
+  const uint32_t S = p.nstages;
+  const uint32_t bar_full = ring0 + S * p.stage_bytes, bar_empty = bar_full + 8 * S;
+  const unsigned nwarps_active = p.rps * p.tiles_per_row;
+  if (threadIdx.x == 0) {
+    for (uint32_t i = 0; i < S; i++) {
+      mbar_init(bar_full + 8 * i, p.nrows);
+      mbar_init(bar_empty + 8 * i, nwarps_active);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - (0x4B000000u << (2 + RL2));
+  const float clamp_lo = p.clamp_lo;
+  DecodeK2 k;
+  k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
+  k.kC = pk(-(8388608.0f + 128.0f), -(8388608.0f + 128.0f));
+  k.inv255 = pk(p.m.inv255, p.m.inv255);
+  k.ys = pk(p.m.ys, p.m.ys);
+  k.g_cb = pk(p.m.g_cb, p.m.g_cb);
+  k.b_cb = pk(p.m.b_cb, p.m.b_cb);
+  k.r_cr = pk(p.m.r_cr, p.m.r_cr);
+  k.g_cr = pk(p.m.g_cr, p.m.g_cr);
+  k.fN = pk((float) N, (float) N);
+  k.magic = pk(8388608.0f, 8388608.0f);
+  k.one = pk(p.one, p.one);
+
+  if (warp >= nwarps_active) return;  // spare warps
+  const unsigned rows2 = p.rows2, rps = p.rps, w = p.w;
+  const unsigned total_rp = (unsigned) p.nframes * rows2;
+  const unsigned nbands = (total_rp + rps - 1) / rps;
+  if (blockIdx.x >= nbands) return;
+  const unsigned nsteps = (nbands - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const unsigned r_local = warp / p.tiles_per_row;
+  const unsigned tile = warp - r_local * p.tiles_per_row;
+
+  // ---- producer role: lane 0 of warp j feeds row j of every stage
+  const bool producer = lane == 0 && warp < (unsigned) p.nrows;
+  unsigned prow_rr = 0, prow_dst = 0;          // row pair within the band; byte offset within a stage
+  const uint8_t *pbase = nullptr;              // plane base
+  unsigned pstride = 0, ppitch = 0, prow_mul = 0, prow_add = 0;  // frame stride; pitch; row = rp*mul + add
+  if (producer) {
+    const unsigned j = warp;
+    if (j < 2 * rps) {
+      prow_rr = j >> 1; pbase = p.y; pstride = (unsigned) p.sy; ppitch = (unsigned) p.py; prow_mul = 2; prow_add = j & 1;
+    } else if (j < 3 * rps) {
+      prow_rr = j - 2 * rps; pbase = p.c; pstride = (unsigned) p.sc; ppitch = (unsigned) p.pc; prow_mul = 1; prow_add = 0;
+    } else {
+      const unsigned q = j - 3 * rps;
+      prow_rr = q >> 1; pbase = p.a; pstride = (unsigned) p.sa; ppitch = (unsigned) p.pa; prow_mul = 2; prow_add = q & 1;
+    }
+    prow_dst = j * w;
+  }
+  auto produce = [&](unsigned kp) {
+    if (!producer || kp >= nsteps) return;
+    const uint32_t slot = kp % S;
+    if (kp >= S) mbar_wait(bar_empty + 8 * slot, ((kp / S) - 1) & 1);
+    const unsigned rpg = (blockIdx.x + kp * gridDim.x) * rps + prow_rr;
+    const uint32_t bar = bar_full + 8 * slot;
+    if (rpg < total_rp) {
+      const unsigned f = rpg / rows2, rp = rpg - f * rows2;
+      const uint8_t *src = ptr_mad(ptr_mad(pbase, f, pstride), rp * prow_mul + prow_add, ppitch);
+      mbar_expect_tx(bar, w);
+      bulk_g2s(ring0 + slot * p.stage_bytes + prow_dst, src, w, bar);
+    } else {
+      mbar_arrive(bar);  // band runs past the last row pair: nothing to copy for this row
+    }
+  };
+
+  // ---- consumer role
+  const unsigned col4 = tile * 32 + lane;
+  const uint32_t my_y = 2 * r_local * w + col4 * 4;              // byte offsets within a stage
+  const uint32_t my_c = (2 * rps + r_local) * w + col4 * 4;
+  const uint32_t my_a = (3 * rps + 2 * r_local) * w + col4 * 4;
+  unsigned rpg = blockIdx.x * rps + r_local;
+  unsigned f0 = rpg / rows2, rp = rpg - f0 * rows2;
+  unsigned oo = f0 * p.so16 + rp * 2 * p.po16 + col4;
+
+  for (unsigned kp = 0; kp + 1 < S; kp++) produce(kp);
+  for (unsigned kk = 0; kk < nsteps; kk++) {
+    produce(kk + S - 1);
+    const uint32_t slot = kk % S;
+    mbar_wait(bar_full + 8 * slot, (kk / S) & 1);
+    const uint32_t st = ring0 + slot * p.stage_bytes;
+    TileLoad<ALPHA> t;
+    t.y0 = lds_u32(st + my_y);
+    t.y1 = lds_u32(st + my_y + w);
+    t.c = lds_u32(st + my_c);
+    if (ALPHA) {
+      t.a0 = lds_u32(st + my_a);
+      t.a1 = lds_u32(st + my_a + w);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
+    if (rpg < total_rp) tile_compute_store<CL2, RL2, ALPHA, true>(p, oo, rp, true, t, k, clamp_lo, sbase);
+    // advance to this warp's row pair in the CTA's next band
+    rpg += p.step_rp;
+    rp += p.d_rp;
+    oo += p.dout;
+    if (rp >= rows2) { rp -= rows2; oo += p.wout; }
+  }
+}
+
+// ========================================================================= decode, generic
+// Any width/height/pitch/alignment (odd sizes, unaligned planes): one thread per 2x2 block,
+// byte accesses, LUT read through the read-only path.  Same arithmetic, same results.
+template <bool ALPHA>
+__global__ void __launch_bounds__(256) k_decode_generic(const DecodeArgs p) {
+  const int cw = (p.w + 1) >> 1;
+  const long long blocks = (long long) p.nframes * p.rows2 * cw;
+  const float fN = (float) (1 << p.cells_log2);
+  const float kY = 16.0f, kC = 128.0f;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < blocks;
+       i += (long long) gridDim.x * blockDim.x) {
+    const int bx = (int) (i % cw);
+    const long long t = i / cw;
+    const int rp = (int) (t % p.rows2);
+    const long long f = t / p.rows2;
+    const uint8_t *cp = p.c + f * p.sc + (long long) rp * p.pc + bx * 2;
+    float cbn = __fmul_rn((float) cp[0] - kC, p.m.inv255);
+    float crn = __fmul_rn((float) cp[1] - kC, p.m.inv255);
+    float cb_g = __fmul_rn(cbn, p.m.g_cb), cb_b = __fmul_rn(cbn, p.m.b_cb);
+    float cr_r = __fmul_rn(crn, p.m.r_cr), cr_g = __fmul_rn(crn, p.m.g_cr);
+    for (int dy = 0; dy < 2; dy++) {
+      const int row = rp * 2 + dy;
+      if (row >= p.h) break;
+      for (int dx = 0; dx < 2; dx++) {
+        const int col = bx * 2 + dx;
+        if (col >= p.w) break;
+        float yf = (float) p.y[f * p.sy + (long long) row * p.py + col] - kY;
+        float yt = __fmul_rn(__fmul_rn(yf, p.m.inv255), p.m.ys);
+        float xr = add_sat(yt, cr_r);
+        float xg = add_sat(__fadd_rn(yt, cb_g), cr_g);
+        float xb = add_sat(yt, cb_b);
+        uint32_t R = lut_code(p.lut, xr, p.clamp_lo, fN);
+        uint32_t G = lut_code(p.lut, xg, p.clamp_lo, fN);
+        uint32_t B = lut_code(p.lut, xb, p.clamp_lo, fN);
+        uint32_t A = 255;
+        if (ALPHA) {
+          float af = (float) p.a[f * p.sa + (long long) row * p.pa + col] - kY;
+          float an = add_sat(__fmul_rn(__fmul_rn(af, p.m.inv255), p.m.ys), 0.0f);
+          A = (uint32_t) round_pos(__fmul_rn(an, 255.0f));
+        }
+        uint8_t *o = p.out + f * p.so + (long long) row * p.po + (long long) col * 4;
+        o[0] = (uint8_t) B; o[1] = (uint8_t) G; o[2] = (uint8_t) R; o[3] = (uint8_t) A;
+      }
+    }
+  }
+}
+
+#ifndef BT709_DECODE_THREADS
+#define BT709_DECODE_THREADS 1024
+#endif
+constexpr int kDecodeThreads = BT709_DECODE_THREADS;
+#ifndef BT709_PREFETCH_DEPTH
+#define BT709_PREFETCH_DEPTH 3
+#endif
+constexpr int kPrefetchDepth = BT709_PREFETCH_DEPTH;  // steps the loads run ahead of the math
+#ifndef BT709_RING_DEPTH
+#define BT709_RING_DEPTH 2
+#endif
+constexpr int kRingDepth = BT709_RING_DEPTH;  // stages of the per-warp cp.async ring
+
+template <int CL2, int RL2, bool ALPHA, bool FULL, bool WRAP>
+static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
+  constexpr size_t smem = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
+  auto k = k_decode_fast<CL2, RL2, ALPHA, FULL, WRAP, kPrefetchDepth, kDecodeThreads>;
+  auto kring = k_decode_ring<CL2, RL2, ALPHA, WRAP, kRingDepth, kDecodeThreads>;
+  constexpr size_t smem_ring = smem + (size_t) (kDecodeThreads / 32) * kRingDepth * (ALPHA ? 640 : 384);
+  static const bool no_ring = getenv("BT709_NO_RING") != nullptr;
+  const bool use_ring = FULL && !no_ring && aligned(a0.y, 16) && aligned(a0.py, 16) && aligned(a0.sy, 16) &&
+                        aligned(a0.c, 16) && aligned(a0.pc, 16) && aligned(a0.sc, 16) &&
+                        (!ALPHA || (aligned(a0.a, 16) && aligned(a0.pa, 16) && aligned(a0.sa, 16)));
+  // frames per launch such that every 32-bit unit offset stays below 2^32
+  const unsigned long long lim = 0xFFFF0000ull;
+  unsigned long long per = lim;
+  auto fit = [&](long long stride, unsigned unit, long long frame_bytes) {
+    if (stride <= 0) return;
+    unsigned long long n = (lim * unit - (unsigned long long) frame_bytes) / (unsigned long long) stride + 1;
+    if (n < per) per = n;
+  };
+  fit(a0.sy, 4, (long long) a0.h * a0.py);
+  fit(a0.sc, 4, (long long) a0.rows2 * a0.pc);
+  fit(a0.so, 16, (long long) a0.h * a0.po);
+  if (ALPHA) fit(a0.sa, 4, (long long) a0.h * a0.pa);
+  if (per < 1) per = 1;
+  if (a0.nframes == 1) {
+    // one (possibly very tall) image: split by rows instead, in chunks whose offsets fit in 32 bits
+    const unsigned long long out_bytes = (unsigned long long) a0.h * a0.po;
+    if (out_bytes > lim * 16 || (unsigned long long) a0.h * a0.py > lim * 4) {
+      long long rows_per = (long long) ((lim * 16) / (unsigned long long) a0.po);
+      if ((unsigned long long) rows_per * a0.py > lim * 4) rows_per = (long long) ((lim * 4) / (unsigned long long) a0.py);
+      rows_per &= ~1ll;
+      for (long long r0 = 0; r0 < a0.h; r0 += rows_per) {
+        DecodeArgs a = a0;
+        a.h = (int) (a0.h - r0 < rows_per ? a0.h - r0 : rows_per);
+        a.rows2 = (a.h + 1) / 2;
+        a.y = a0.y + r0 * a0.py;
+        a.c = a0.c + (r0 / 2) * a0.pc;
+        a.out = a0.out + r0 * a0.po;
+        if (ALPHA) a.a = a0.a + r0 * a0.pa;
+        int e = launch_decode_fast2<CL2, RL2, ALPHA, FULL, WRAP>(a, sm_count, s);
+        if (e) return e;
+      }
+      return 0;
+    }
+  }
+  for (int f0 = 0; f0 < a0.nframes; f0 += (int) per) {
+    DecodeArgs a = a0;
+    a.nframes = (int) ((unsigned long long) (a0.nframes - f0) < per ? (unsigned long long) (a0.nframes - f0) : per);
+    a.y = a0.y + (long long) f0 * a0.sy;
+    a.c = a0.c + (long long) f0 * a0.sc;
+    a.out = a0.out + (long long) f0 * a0.so;
+    if (ALPHA) a.a = a0.a + (long long) f0 * a0.sa;
+    const unsigned total_rp = (unsigned) a.nframes * a.rows2;
+    unsigned grid = (total_rp + a.rps - 1) / a.rps;
+    if (grid > (unsigned) sm_count) grid = sm_count;
+    // per-step increments of the unit offsets, and the extra increment on a frame wrap (mod 2^32)
+    a.step_rp = grid * a.rps;
+    const unsigned d_f = a.step_rp / a.rows2;
+    a.d_rp = a.step_rp - d_f * a.rows2;
+    a.py4 = (unsigned) (a.py / 4); a.pc4 = (unsigned) (a.pc / 4); a.pa4 = (unsigned) (a.pa / 4); a.po16 = (unsigned) (a.po / 16);
+    a.sy4 = (unsigned) (a.sy / 4); a.sc4 = (unsigned) (a.sc / 4); a.sa4 = (unsigned) (a.sa / 4); a.so16 = (unsigned) (a.so / 16);
+    a.dy = d_f * a.sy4 + a.d_rp * 2 * a.py4;
+    a.dc = d_f * a.sc4 + a.d_rp * a.pc4;
+    a.da = d_f * a.sa4 + a.d_rp * 2 * a.pa4;
+    a.dout = d_f * a.so16 + a.d_rp * 2 * a.po16;
+    a.wy = a.sy4 - a.rows2 * 2 * a.py4;
+    a.wc = a.sc4 - a.rows2 * a.pc4;
+    a.wa = a.sa4 - a.rows2 * 2 * a.pa4;
+    a.wout = a.so16 - a.rows2 * 2 * a.po16;
+    if (use_ring)
+      kring<<<grid, kDecodeThreads, smem_ring, s>>>(a);
+    else
+      k<<<grid, kDecodeThreads, smem, s>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return (int) e;
+  }
+  return 0;
+}
+
+
+template <int CL2, int RL2, bool ALPHA>
+static bool bulk_ok(const DecodeArgs &a, int *nstages, int *stage_bytes, int *nrows) {
+  constexpr size_t lut = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
+  const int wpc = kDecodeThreads / 32;
+  if (!(a.w % 128 == 0 && a.h % 2 == 0 && a.tiles_per_row <= wpc)) return false;
+  if (!(aligned(a.y, 16) && aligned(a.py, 16) && aligned(a.sy, 16) && aligned(a.c, 16) && aligned(a.pc, 16) &&
+        aligned(a.sc, 16)))
+    return false;
+  if (ALPHA && !(aligned(a.a, 16) && aligned(a.pa, 16) && aligned(a.sa, 16))) return false;
+  *nrows = (ALPHA ? 5 : 3) * a.rps;
+  if (*nrows > a.rps * a.tiles_per_row) return false;  // one producer lane per row
+  *stage_bytes = *nrows * a.w;
+  long long room = (long long) kMaxDynSmem - (long long) lut - 16 * 8 * 2;
+  int n = (int) (room / *stage_bytes);
+  if (n > 8) n = 8;
+  if (n < 2) return false;
+  *nstages = n;
+  return true;
+}
+
+template <int CL2, int RL2, bool ALPHA>
+static int launch_decode_fast(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
+  DecodeArgs a = a0;
+  int nstages = 0, stage_bytes = 0, nrows = 0;
+  // The bulk-staged variant is correct (tests/test_gpu_decode.py runs it) but measured slower than
+  // per-thread loads (774 vs 811 Gpix/s on 600 x 1080p): the path is bound by HBM *write*
+  // bandwidth (profiles/r01_membw_probe.json), not by read latency.  Opt-in for reproduction.
+  static const bool use_bulk = getenv("BT709_BULK") != nullptr;
+  if (use_bulk && bulk_ok<CL2, RL2, ALPHA>(a, &nstages, &stage_bytes, &nrows)) {
+    constexpr size_t lut = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
+    a.nstages = nstages; a.stage_bytes = stage_bytes; a.nrows = nrows;
+    const size_t smem = lut + (size_t) nstages * stage_bytes + (size_t) nstages * 16;
+    // the output offsets are 32-bit in 16-byte units: split batches that would overflow
+    const unsigned long long lim = 0xFFFF0000ull;
+    unsigned long long per = a.so > 0 ? (lim * 16 - (unsigned long long) a.h * a.po) / (unsigned long long) a.so + 1 : lim;
+    if (per < 1) per = 1;
+    for (int f0 = 0; f0 < a0.nframes; f0 += (int) per) {
+      a.nframes = (int) ((unsigned long long) (a0.nframes - f0) < per ? (unsigned long long) (a0.nframes - f0) : per);
+      a.y = a0.y + (long long) f0 * a0.sy;
+      a.c = a0.c + (long long) f0 * a0.sc;
+      a.out = a0.out + (long long) f0 * a0.so;
+      if (ALPHA) a.a = a0.a + (long long) f0 * a0.sa;
+      const unsigned total_rp = (unsigned) a.nframes * a.rows2;
+      unsigned grid = (total_rp + a.rps - 1) / a.rps;
+      if (grid > (unsigned) sm_count) grid = sm_count;
+      a.step_rp = grid * a.rps;
+      const unsigned d_f = a.step_rp / a.rows2;
+      a.d_rp = a.step_rp - d_f * a.rows2;
+      a.po16 = (unsigned) (a.po / 16); a.so16 = (unsigned) (a.so / 16);
+      a.dout = d_f * a.so16 + a.d_rp * 2 * a.po16;
+      a.wout = a.so16 - a.rows2 * 2 * a.po16;
+      k_decode_bulk<CL2, RL2, ALPHA, kDecodeThreads><<<grid, kDecodeThreads, smem, s>>>(a);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return (int) e;
+    }
+    return 0;
+  }
+  const bool full = (a.w % 128 == 0) && (a.h % 2 == 0);
+  if (!full) return launch_decode_fast2<CL2, RL2, ALPHA, false, true>(a, sm_count, s);
+  // contiguous frames: decode the batch as one tall image (no frame seams to step across)
+  const bool contiguous = a.nframes == 1 || (a.sy == (long long) a.h * a.py && a.sc == (long long) a.rows2 * a.pc &&
+                                             a.so == (long long) a.h * a.po && (!ALPHA || a.sa == (long long) a.h * a.pa));
+  if (contiguous && (long long) a.nframes * a.h < (1ll << 30)) {
+    a.h *= a.nframes;
+    a.rows2 *= a.nframes;
+    a.nframes = 1;
+    return launch_decode_fast2<CL2, RL2, ALPHA, true, false>(a, sm_count, s);
+  }
+  return launch_decode_fast2<CL2, RL2, ALPHA, true, true>(a, sm_count, s);
+}
+
+int launch_decode(const DecodeArgs &a0, int sm_count, void *stream) {
+  cudaStream_t s = (cudaStream_t) stream;
+  DecodeArgs a = a0;
+  a.rows2 = (a.h + 1) / 2;
+  // 128-pixel tiles; the CTA's warps cover rps whole row pairs per step (see k_decode_fast)
+  a.tiles_per_row = (a.w + 127) / 128;
+  const int wpc = kDecodeThreads / 32;
+  a.rps = a.tiles_per_row >= wpc ? 1 : wpc / a.tiles_per_row;
+  a.tile_stride = a.tiles_per_row >= wpc ? wpc : a.tiles_per_row;  // > 4096 px wide: warps loop over tiles
+  const bool alpha = a.a != nullptr;
+  const unsigned long long units = (unsigned long long) a.nframes * a.rows2 + 2ull * sm_count * 32;
+  bool fast = (a.w % 4 == 0) && aligned(a.y, 4) && aligned(a.py, 4) && aligned(a.sy, 4) && aligned(a.c, 4) &&
+              aligned(a.pc, 4) && aligned(a.sc, 4) && aligned(a.out, 16) && aligned(a.po, 16) &&
+              aligned(a.so, 16) && units < 0x7FFFFFFFull && a.sy < (1ll << 32) && a.sc < (1ll << 32) &&
+              a.so < (1ll << 34) && a.sa < (1ll << 32) && a.py < (1ll << 28) && a.pc < (1ll << 28) && a.po < (1ll << 30) &&
+              a.pa < (1ll << 28) && a.sy >= 0 && a.sc >= 0 && a.so >= 0 && a.sa >= 0 &&
+              (a.cells_log2 == 10 || a.cells_log2 == 12);
+  if (alpha) fast = fast && aligned(a.a, 4) && aligned(a.pa, 4) && aligned(a.sa, 4);
+  if (fast) {
+    if (a.cells_log2 == 10)
+      return alpha ? launch_decode_fast<10, 5, true>(a, sm_count, s) : launch_decode_fast<10, 5, false>(a, sm_count, s);
+    return alpha ? launch_decode_fast<12, 3, true>(a, sm_count, s) : launch_decode_fast<12, 3, false>(a, sm_count, s);
+  }
+  const long long blocks = (long long) a.nframes * a.rows2 * ((a.w + 1) / 2);
+  long long grid = (blocks + 255) / 256;
+  if (grid > (long long) sm_count * 16) grid = (long long) sm_count * 16;
+  if (alpha)
+    k_decode_generic<true><<<(unsigned) grid, 256, 0, s>>>(a);
+  else
+    k_decode_generic<false><<<(unsigned) grid, 256, 0, s>>>(a);
+  return (int) cudaGetLastError();
+}
+
+template <int CL2, int RL2, bool ALPHA>
+static int optin_decode_smem() {
+  constexpr size_t smem = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
+  int e = (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, true, true, kPrefetchDepth, kDecodeThreads>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, true, false, kPrefetchDepth, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_ring<CL2, RL2, ALPHA, true, kRingDepth, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_ring<CL2, RL2, ALPHA, false, kRingDepth, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_bulk<CL2, RL2, ALPHA, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  return (int) cudaFuncSetAttribute(k_decode_fast<CL2, RL2, ALPHA, false, true, kPrefetchDepth, kDecodeThreads>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+}
+
+// per device (called from bt709_ctx_create with the device current): opt in to > 48 KB of dynamic
+// shared memory for the replicated-LUT decode kernels
+int decode_kernels_init() {
+  int e;
+  if ((e = optin_decode_smem<10, 5, false>())) return e;
+  if ((e = optin_decode_smem<10, 5, true>())) return e;
+  if ((e = optin_decode_smem<12, 3, false>())) return e;
+  if ((e = optin_decode_smem<12, 3, true>())) return e;
+  return 0;
+}
+
+}  // namespace bt709

@@ -1,0 +1,318 @@
+// bt709_encode.cu — inverse path: sRGB BGRA8 -> BT.709 4:2:0 NV12 with 2x2 linear-light chroma
+// averaging (cvpbu_ycbcr_subsample + BT709_average_pixel_values).
+#include "bt709_device.cuh"
+
+namespace bt709 {
+
+// ================================================================================== encode
+// cvpbu_ycbcr_subsample + BT709_average_pixel_values (CVPixelBufferUtils.h:284-363,
+// BT709.h:1349-1509).  VEC: one thread = 4 px x 2 rows (two 2x2 blocks), 16-byte loads,
+// 4-byte Y and CbCr stores, so a warp reads 512 B and writes 128 B per row contiguously.
+// !VEC: one thread per 2x2 block, 4-byte loads and byte stores (any even size / pitch).
+struct EncTables {
+  const float *lin;      // shared
+  const float *compn;    // shared
+  const uint32_t *olut;  // shared
+  float clamp_lo, fN;
+};
+
+__device__ __forceinline__ uint32_t enc_luma(uint32_t px, const EncTables &t) {
+  // per-pixel: requantised output-gamma RGB (BT709.h:1472-1476) -> matrix (BT709.h:223, 234, 245)
+  float rn = t.compn[(px >> 16) & 255], gn = t.compn[(px >> 8) & 255], bn = t.compn[px & 255];
+  float ey = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, rn), __fmul_rn(0.7152f, gn)), __fmul_rn(0.0722f, bn));
+  return (uint32_t) round_pos(__fadd_rn(__fmul_rn(ey, 219.0f), 16.0f));
+}
+
+__device__ __forceinline__ uint32_t enc_chroma(uint32_t p1, uint32_t p2, uint32_t p3, uint32_t p4, const EncTables &t) {
+  // mean in linear light (BT709.h:1400-1409), requantise in the output gamma (:1418-1420),
+  // matrix on the 8-bit values (:1426 -> :223-247).  Returns Cb | Cr << 8.
+  float q[3];
+#pragma unroll
+  for (int ch = 0; ch < 3; ch++) {
+    const int sh = 16 - ch * 8;  // R, G, B
+    float s = __fadd_rn(__fadd_rn(__fadd_rn(t.lin[(p1 >> sh) & 255], t.lin[(p2 >> sh) & 255]), t.lin[(p3 >> sh) & 255]),
+                        t.lin[(p4 >> sh) & 255]);
+    float mean = __fmul_rn(s, 0.25f);  // "/ 4.0f" is exact
+    uint32_t code = lut_code(t.olut, mean, t.clamp_lo, t.fN);
+    q[ch] = __fmul_rn((float) code, 1.0f / 255.0f);
+  }
+  float ey = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, q[0]), __fmul_rn(0.7152f, q[1])), __fmul_rn(0.0722f, q[2]));
+  float eb = __fdiv_rn(__fsub_rn(q[2], ey), 1.8556f);
+  float er = __fdiv_rn(__fsub_rn(q[0], ey), 1.5748f);
+  uint32_t cb = (uint32_t) round_pos(__fadd_rn(__fmul_rn(eb, 224.0f), 128.0f));
+  uint32_t cr = (uint32_t) round_pos(__fadd_rn(__fmul_rn(er, 224.0f), 128.0f));
+  return cb | (cr << 8);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_encode(const EncodeArgs p) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  float *s_lin = reinterpret_cast<float *>(s_mem);
+  float *s_compn = s_lin + 256;
+  uint32_t *s_olut = s_mem + 512;
+  const int nl = (1 << p.out_cells_log2) + 1;
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+    s_lin[i] = __ldg(&p.lin256[i]);
+    s_compn[i] = __ldg(&p.compn256[i]);
+  }
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) s_olut[i] = __ldg(&p.out_lut[i]);
+  __syncthreads();
+  EncTables t{s_lin, s_compn, s_olut, p.out_clamp_lo, (float) (1 << p.out_cells_log2)};
+
+  const int bw = VEC ? p.w / 4 : p.w / 2;  // thread tiles per row pair
+  const int rows2 = p.h / 2;
+  const long long n = (long long) p.nframes * rows2 * bw;
+  for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long) gridDim.x * blockDim.x) {
+    const int bx = (int) (i % bw);
+    const long long r = i / bw;
+    const int rp = (int) (r % rows2);
+    const long long f = r / rows2;
+    const uint8_t *in0 = p.in + f * p.si + (long long) (2 * rp) * p.pi;
+    const uint8_t *in1 = in0 + p.pi;
+    uint8_t *y0 = p.y + f * p.sy + (long long) (2 * rp) * p.py;
+    uint8_t *y1 = y0 + p.py;
+    uint8_t *c = p.c + f * p.sc + (long long) rp * p.pc;
+    if (VEC) {
+      const uint4 a = ld_stream_u128(in0 + (long long) bx * 16);
+      const uint4 b = ld_stream_u128(in1 + (long long) bx * 16);
+      uint32_t yw0 = enc_luma(a.x, t) | (enc_luma(a.y, t) << 8) | (enc_luma(a.z, t) << 16) | (enc_luma(a.w, t) << 24);
+      uint32_t yw1 = enc_luma(b.x, t) | (enc_luma(b.y, t) << 8) | (enc_luma(b.z, t) << 16) | (enc_luma(b.w, t) << 24);
+      uint32_t cw = enc_chroma(a.x, a.y, b.x, b.y, t) | (enc_chroma(a.z, a.w, b.z, b.w, t) << 16);
+      st_stream_u32(y0 + bx * 4, yw0);
+      st_stream_u32(y1 + bx * 4, yw1);
+      st_stream_u32(c + bx * 4, cw);
+    } else {
+      const uint32_t *r0 = reinterpret_cast<const uint32_t *>(in0) + bx * 2;
+      const uint32_t *r1 = reinterpret_cast<const uint32_t *>(in1) + bx * 2;
+      const uint32_t p1 = __ldg(r0), p2 = __ldg(r0 + 1), p3 = __ldg(r1), p4 = __ldg(r1 + 1);
+      y0[bx * 2] = (uint8_t) enc_luma(p1, t);
+      y0[bx * 2 + 1] = (uint8_t) enc_luma(p2, t);
+      y1[bx * 2] = (uint8_t) enc_luma(p3, t);
+      y1[bx * 2 + 1] = (uint8_t) enc_luma(p4, t);
+      const uint32_t cc = enc_chroma(p1, p2, p3, p4, t);
+      c[bx * 2] = (uint8_t) (cc & 255);
+      c[bx * 2 + 1] = (uint8_t) (cc >> 8);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------- encode, fast
+// Same arithmetic as k_encode, organised like the decode: persistent CTAs of 1024 threads, a warp
+// owns a 128-pixel x 2-row tile (lane l: pixels 4l..4l+3 of both rows = two 2x2 blocks), the warps
+// of a CTA cover whole row pairs (bands), addresses are 32-bit unit offsets.  Per warp step:
+// 2 x LDG.128 (512 B per row), 2 x STG.32 of Y (128 B per row), 1 x STG.32 of CbCr (128 B).
+//   * both 256-entry byte tables are merged into one {linear, requantised/255} float2 table with one
+//     8-byte replica per lane (entry stride 256 B), so the LDS.64 gathers are conflict-free and the
+//     address (byte << 8) | (lane << 3) is a single PRMT of the pixel word and the lane register;
+//   * float32 steps run two at a time on the packed FADD2/FMUL2/FFMA2 pipe.  ptxas contracts a
+//     packed multiply feeding a packed add into one FFMA2 (one rounding instead of two), so every
+//     add that follows a multiply is written fma(product, one, addend) with a run-time 1.0;
+//   * x / 1.8556f and x / 1.5748f are q0 = x*rc; r = fma(-q0, c, x); q = fma(r, rc, q0), which equals
+//     the IEEE quotient for every value this path can produce (all 2^24 8-bit RGB triples checked
+//     on the host: tests/test_tables_cpu.py) and costs 3 instructions instead of ~10;
+//   * round() of the positive results is add.rz(+0.5) then add.rz(+2^23): the code is the low byte.
+struct EncK {
+  f32x2 one, kr, kg, kb, s219, o16, s224, o128, rcb, ncb, rcr, ncr, quarter, half, magic, inv255, nmagic;
+};
+
+__device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// exact a + b where a (or b) may be the result of a packed multiply: never contracted
+__device__ __forceinline__ f32x2 add2_nc(f32x2 a, f32x2 b, const EncK &k) { return fma2_rn(a, k.one, b); }
+
+// Ey of BT709.h:223 for two pixels, then round(Ey*219 + 16) (BT709.h:234, 245): magic floats 2^23 + Y
+__device__ __forceinline__ f32x2 enc_luma2(f32x2 rn, f32x2 gn, f32x2 bn, const EncK &k) {
+  f32x2 ey = add2_nc(add2_nc(mul2(k.kr, rn), mul2(k.kg, gn), k), mul2(k.kb, bn), k);
+  f32x2 ay = add2_nc(mul2(ey, k.s219), k.o16, k);
+  return add2_rz(add2_rz(ay, k.half), k.magic);
+}
+
+template <bool WRAP>
+__global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  // [0, 64 KB): float2 table, entry b replica r at byte b*256 + r*8;  then the chroma cell LUT
+  float2 *s_tab = reinterpret_cast<float2 *>(s_mem);
+  uint32_t *s_olut = s_mem + 256 * 64;
+  const int nl = (1 << p.out_cells_log2) + 1;
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+    const int b = i >> 5;
+    s_tab[i] = make_float2(__ldg(&p.lin256[b]), __ldg(&p.compn256[b]));
+  }
+  // chroma cell LUT replicated 8x (entry i replica r at word i*8 + r): random means otherwise
+  // cost ~3 wavefronts per lookup and the kernel is bound by shared-memory bandwidth
+  for (int i = threadIdx.x; i < nl * 8; i += blockDim.x) s_olut[i] = __ldg(&p.out_lut[i >> 3]);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t tab = (uint32_t) __cvta_generic_to_shared(s_tab);  // warp-uniform
+  const uint32_t lane8 = lane << 3;
+  const uint32_t olut = (uint32_t) __cvta_generic_to_shared(s_olut) + ((lane & 7) << 2) - (0x4B000000u << 5);
+  const float clamp_lo = p.out_clamp_lo;
+  const float fN = (float) (1 << p.out_cells_log2);
+  EncK k;
+  auto bc = [](float v) { return pk(v, v); };
+  k.one = bc(p.one); k.kr = bc(0.2126f); k.kg = bc(0.7152f); k.kb = bc(0.0722f);
+  k.s219 = bc(219.0f); k.o16 = bc(16.0f); k.s224 = bc(224.0f); k.o128 = bc(128.0f);
+  k.rcb = bc(1.0f / 1.8556f); k.ncb = bc(-1.8556f); k.rcr = bc(1.0f / 1.5748f); k.ncr = bc(-1.5748f);
+  k.quarter = bc(0.25f); k.half = bc(0.5f); k.magic = bc(8388608.0f); k.nmagic = bc(-8388608.0f);
+  k.inv255 = bc(1.0f / 255.0f);
+
+  const unsigned r_local = warp / p.tiles_per_row;
+  if (r_local >= (unsigned) p.rps) return;
+  const unsigned tile = warp - r_local * p.tiles_per_row;
+  const unsigned rows2 = p.h / 2;
+  const unsigned total_rp = (unsigned) p.nframes * rows2;
+  const unsigned rpg0 = blockIdx.x * p.rps + r_local;
+  if (rpg0 >= total_rp) return;
+  const unsigned f0 = rpg0 / rows2, rp0 = rpg0 - f0 * rows2;
+  const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;
+  const unsigned col4 = tile * 32 + lane;
+  unsigned oi = f0 * p.si16 + rp0 * 2 * p.pi16 + col4;  // BGRA in, 16-byte units
+  unsigned oy = f0 * p.sy4 + rp0 * 2 * p.py4 + col4;    // Y out, 4-byte units
+  unsigned oc = f0 * p.sc4 + rp0 * p.pc4 + col4;        // CbCr out, 4-byte units
+  unsigned rp = rp0;
+
+  auto fetch = [&](uint32_t px, int shift, float &lin, float &cn) {
+    // table offset (byte << 8) | (lane << 3): byte 1 = the pixel's channel byte, byte 0 = lane * 8
+    const uint32_t off = __byte_perm(px, lane8, shift == 16 ? 0x7724 : shift == 8 ? 0x7714 : 0x7704);  // bytes 2,3 = 0 (upper bytes of lane8)
+    float2 v;
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(tab + off));
+    lin = v.x;
+    cn = v.y;
+  };
+  auto code_of = [&](float mean) -> float {  // BT709_from_linear code as a magic float 2^23 + code
+    float xc = fmaxf(mean, clamp_lo), t;
+    asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(t) : "f"(xc), "f"(fN));
+    uint32_t e;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((__float_as_uint(t) << 5) + olut));
+    return __uint_as_float(__byte_perm(e + __float_as_uint(xc), 0x4B000000u, 0x7543));
+  };
+
+  // one-step register prefetch: the loads of step k+1 are issued before the math of step k
+  // (without it 40 % of the warp samples sat on the first use of the loaded pixels)
+  unsigned rpl = rp0;
+  uint4 na = ld_stream_u128(ptr_mad(p.in, oi, 16));
+  uint4 nb = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
+  for (unsigned kk = 0; kk < nsteps; kk++) {
+    const uint4 a = na, b = nb;
+    rpl += p.d_rp;
+    oi += p.di;
+    if (WRAP && rpl >= rows2) { rpl -= rows2; oi += p.wi; }
+    if (kk + 1 < nsteps) {
+      na = ld_stream_u128(ptr_mad(p.in, oi, 16));
+      nb = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
+    }
+    // Walk the four pixel pairs in the order NW, NE (row 0), SW, SE (row 1): pair (0,2) holds the
+    // west pixels of blocks A and B, pair (1,3) the east pixels.  Luma is finished per pair; the
+    // linear-light sums accumulate in the reference's order ((NW + NE) + SW) + SE (BT709.h:1182-1183).
+    uint32_t yw[2];
+    f32x2 sum[3];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+      const uint32_t p0 = r ? b.x : a.x, p1 = r ? b.y : a.y, p2 = r ? b.z : a.z, p3 = r ? b.w : a.w;
+      f32x2 m[2];
+#pragma unroll
+      for (int e = 0; e < 2; e++) {  // e = 0: pixels (0,2); e = 1: pixels (1,3)
+        const uint32_t pw = e ? p1 : p0, pe = e ? p3 : p2;
+        float lw[3], cw_[3], le[3], ce[3];
+        fetch(pw, 16, lw[0], cw_[0]); fetch(pw, 8, lw[1], cw_[1]); fetch(pw, 0, lw[2], cw_[2]);
+        fetch(pe, 16, le[0], ce[0]); fetch(pe, 8, le[1], ce[1]); fetch(pe, 0, le[2], ce[2]);
+        m[e] = enc_luma2(pk(cw_[0], ce[0]), pk(cw_[1], ce[1]), pk(cw_[2], ce[2]), k);
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) {
+          const f32x2 v = pk(lw[ch], le[ch]);
+          sum[ch] = (r == 0 && e == 0) ? v : add2(sum[ch], v);
+        }
+      }
+      uint32_t y0, y1, y2, y3;
+      upku(m[0], y0, y2); upku(m[1], y1, y3);
+      yw[r] = __byte_perm(__byte_perm(y0, y1, 0x0040), __byte_perm(y2, y3, 0x0040), 0x5410);
+    }
+    // ---- chroma of blocks A and B: mean, requantise to 8 bits in the output gamma
+    // (BT709.h:1418-1420), back to unorm (sRGB.h:32-36)
+    f32x2 q[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ch++) {
+      float mA, mB;
+      upk(mul2(sum[ch], k.quarter), mA, mB);
+      q[ch] = mul2(add2(pk(code_of(mA), code_of(mB)), k.nmagic), k.inv255);
+    }
+    f32x2 ey = add2_nc(add2_nc(mul2(k.kr, q[0]), mul2(k.kg, q[1]), k), mul2(k.kb, q[2]), k);
+    f32x2 xb = add2(q[2], mul2(ey, bc(-1.0f))), xr = add2(q[0], mul2(ey, bc(-1.0f)));
+    f32x2 qb = mul2(xb, k.rcb), qr = mul2(xr, k.rcr);
+    qb = fma2_rn(fma2_rn(qb, k.ncb, xb), k.rcb, qb);
+    qr = fma2_rn(fma2_rn(qr, k.ncr, xr), k.rcr, qr);
+    f32x2 mb = add2_rz(add2_rz(add2_nc(mul2(qb, k.s224), k.o128, k), k.half), k.magic);
+    f32x2 mr = add2_rz(add2_rz(add2_nc(mul2(qr, k.s224), k.o128, k), k.half), k.magic);
+    uint32_t cbA, cbB, crA, crB;
+    upku(mb, cbA, cbB); upku(mr, crA, crB);
+    const uint32_t cw = __byte_perm(__byte_perm(cbA, crA, 0x0040), __byte_perm(cbB, crB, 0x0040), 0x5410);
+    st_stream_u32((void *) ptr_mad(p.y, oy, 4), yw[0]);
+    st_stream_u32((void *) ptr_mad(p.y, oy + p.py4, 4), yw[1]);
+    st_stream_u32((void *) ptr_mad(p.c, oc, 4), cw);
+    rp += p.d_rp;
+    oy += p.dy; oc += p.dc;
+    if (WRAP && rp >= rows2) { rp -= rows2; oy += p.wy; oc += p.wc; }
+  }
+}
+
+static int launch_encode_fast(const EncodeArgs &a0, int sm_count, cudaStream_t s) {
+  EncodeArgs a = a0;
+  const int rows2 = a.h / 2;
+  const int wpc = 32;
+  a.tiles_per_row = a.w / 128;
+  a.rps = wpc / a.tiles_per_row;
+  const bool contiguous = a.nframes == 1 || (a.si == (long long) a.h * a.pi && a.sy == (long long) a.h * a.py &&
+                                             a.sc == (long long) rows2 * a.pc);
+  bool wrap = true;
+  if (contiguous) { a.h *= a.nframes; a.nframes = 1; wrap = false; }
+  const unsigned total_rp = (unsigned) a.nframes * (a.h / 2);
+  unsigned grid = (total_rp + a.rps - 1) / a.rps;
+  if (grid > (unsigned) sm_count) grid = sm_count;
+  a.step_rp = grid * a.rps;
+  const unsigned r2 = a.h / 2, d_f = a.step_rp / r2;
+  a.d_rp = a.step_rp - d_f * r2;
+  a.pi16 = (unsigned) (a.pi / 16); a.py4 = (unsigned) (a.py / 4); a.pc4 = (unsigned) (a.pc / 4);
+  a.si16 = (unsigned) (a.si / 16); a.sy4 = (unsigned) (a.sy / 4); a.sc4 = (unsigned) (a.sc / 4);
+  a.di = d_f * a.si16 + a.d_rp * 2 * a.pi16; a.dy = d_f * a.sy4 + a.d_rp * 2 * a.py4; a.dc = d_f * a.sc4 + a.d_rp * a.pc4;
+  a.wi = a.si16 - r2 * 2 * a.pi16; a.wy = a.sy4 - r2 * 2 * a.py4; a.wc = a.sc4 - r2 * a.pc4;
+  a.one = 1.0f;
+  const size_t smem = 65536 + ((size_t) (1 << a.out_cells_log2) + 1) * 32;
+  if (wrap)
+    k_encode_fast<true><<<grid, 1024, smem, s>>>(a);
+  else
+    k_encode_fast<false><<<grid, 1024, smem, s>>>(a);
+  return (int) cudaGetLastError();
+}
+
+int launch_encode(const EncodeArgs &a, int sm_count, void *stream) {
+  cudaStream_t s = (cudaStream_t) stream;
+  const size_t smem = (512 + (size_t) (1 << a.out_cells_log2) + 1) * 4;
+  const bool vec = (a.w % 4 == 0) && aligned(a.in, 16) && aligned(a.pi, 16) && aligned(a.si, 16) && aligned(a.y, 4) &&
+                   aligned(a.py, 4) && aligned(a.sy, 4) && aligned(a.c, 4) && aligned(a.pc, 4) && aligned(a.sc, 4);
+  // fast path: whole 128-pixel tiles, at most 32 tiles per row, offsets that fit 32-bit units
+  const unsigned long long in_bytes = (unsigned long long) a.nframes * (a.si > 0 ? a.si : (long long) a.h * a.pi);
+  if (vec && a.w % 128 == 0 && a.w <= 4096 && in_bytes < 0xFFFF0000ull * 16 && a.si >= 0 && a.sy >= 0 && a.sc >= 0 &&
+      a.out_cells_log2 <= 12)
+    return launch_encode_fast(a, sm_count, s);
+  const long long n = (long long) a.nframes * (a.h / 2) * (vec ? a.w / 4 : a.w / 2);
+  long long grid = (n + 255) / 256;
+  if (grid > (long long) sm_count * 8) grid = (long long) sm_count * 8;
+  if (vec)
+    k_encode<true><<<(unsigned) grid, 256, smem, s>>>(a);
+  else
+    k_encode<false><<<(unsigned) grid, 256, smem, s>>>(a);
+  return (int) cudaGetLastError();
+}
+
+int encode_kernels_init() {
+  int e;
+  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4097 * 32))) return e;
+  return (int) cudaFuncSetAttribute(k_encode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4097 * 32);
+}
+
+}  // namespace bt709

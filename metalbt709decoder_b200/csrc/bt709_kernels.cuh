@@ -1,4 +1,4 @@
-// bt709_kernels.cuh — launch-argument structs shared by the kernels (bt709_kernels.cu)
+// bt709_kernels.cuh — launch-argument structs shared by the kernel translation units (bt709_decode/rescale/encode/misc.cu)
 // and the C ABI (bt709_api.cpp).  Plain PODs, passed by value.
 #pragma once
 #include <cstdint>
@@ -85,7 +85,7 @@ struct PlanarArgs {
   int cw, ch, nframes;
 };
 
-// launchers (bt709_kernels.cu).  Each returns the cudaError_t of the launch.
+// launchers (one per kernel family).  Each returns the cudaError_t of the launch.
 int launch_decode(const DecodeArgs &a, int sm_count, void *stream);
 int launch_rescale(const RescaleArgs &a, int sm_count, void *stream);
 int launch_encode(const EncodeArgs &a, int sm_count, void *stream);
