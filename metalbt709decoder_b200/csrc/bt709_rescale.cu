@@ -68,77 +68,130 @@ __global__ void __launch_bounds__(256) k_rescale(const RescaleArgs p) {
 
 // -------------------------------------------------------------------- rescale, column walker
 // Upscale / same-size fast path (scale <= 1 source pixel per output pixel in both directions).
-// One thread owns one output column over a strip of TH output rows and walks down the source
-// rows it needs: for each source row it converts its two horizontal taps to linear light
-// (256-entry table replicated per lane: conflict-free) and blends them (the oracle's `top`/`bot`,
-// same float32 steps), keeps the two most recent blended rows in registers, and emits every output
-// row that lies between them.  Each blended row is reused by the ~1/scale output rows that touch
-// it, nothing is staged in shared memory, and a warp reads ~96-128 contiguous source bytes and
-// writes 128 contiguous output bytes per row.  The bilinear steps run on packed FADD2/FMUL2/FFMA2.
-constexpr int kRescaleTH = 32;
+// A warp owns a tile of 32 output columns x kWalkTH output rows; a thread owns one output column
+// and walks down the source rows the tile needs.  For each source row it converts its two
+// horizontal taps to linear light (256-entry tables replicated per lane: conflict-free) and blends
+// them (the oracle's `top`/`bot`, same float32 steps), keeps the two most recent blended rows in
+// registers and emits every output row that lies between them, so a blended row is shared by the
+// ~1/scale output rows that touch it.  A warp reads ~96-128 contiguous source bytes and writes 128
+// contiguous output bytes per row; nothing but the tables lives in shared memory.
+//
+// Everything that depends on the output row only (fy, the top source row, the row index)
+// is warp-uniform: the warp computes it once per tile, one row per lane, into its own slice of
+// shared memory, and the row loop reads it back with one LDS.128 per output row.  The walker runs
+// over UNCLAMPED source rows (top row -1 at the upper edge) and clamps only the row it fetches, so
+// the clamped-edge cases of the oracle (both taps on the same row) need no special code.
+//
+// The oracle's clamp01 after the vertical blend is the identity for these operands (for a, b in
+// [0,1] and f in [0,1]: d = RN(b-a), p = RN(f*d), |p| <= |d|, and RN(a+p) stays inside [0,1] because
+// RN(1-a) <= (1-a) + 2^-25 and RN(a-b) <= a), so the blends run on packed FFMA2/FMUL2 without .sat.
+constexpr int kWalkTH = 64;       // output rows per warp tile
+constexpr int kWalkWarps = 32;    // warps per CTA, one CTA per SM
+constexpr int kWalkPD = 3;        // source rows fetched ahead of use
+constexpr int kWalkRowInfo = (kWalkTH + 1) * 4;  // words of row info per warp (one sentinel entry)
 
 struct Lin4 {
   f32x2 rg, ba;  // (R, G), (B, A) in linear light (A is linear already)
 };
 
-__global__ void __launch_bounds__(512, 2) k_rescale_cols(const RescaleArgs p) {
+template <int ERL2>  // log2 of the encode-LUT replication (bank-conflict relief: lanes use replica lane % R)
+__global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const RescaleArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
-  // sRGB byte -> linear float, one replica per lane; entry stride 256 B so that the table offset
-  // (byte << 8) | (lane << 2) is a single PRMT of the texel word and the lane register
-  float *s_lin = reinterpret_cast<float *>(s_mem);  // entry b replica r at word b*64 + r
-  uint32_t *s_enc = s_mem + 256 * 64;
-  const int nenc = (1 << p.enc_cells_log2) + 1;
-  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_lin[(i >> 5) * 64 + (i & 31)] = __ldg(&p.lin256[i >> 5]);
-  for (int i = threadIdx.x; i < nenc; i += blockDim.x) s_enc[i] = __ldg(&p.enc_lut[i]);
+  // Layout (dynamic shared memory, kWalkSmem bytes):
+  //   [lin table, 64 KB, placed at the first 64 KB-ALIGNED shared address]
+  //     word b*64 + r      : sRGB byte b -> linear float, replica r (one per lane)
+  //     word b*64 + 32 + r : alpha byte b -> b * (1/255), replica r
+  //     entry stride 256 B and 64 KB alignment: the lookup address is ONE PRMT of the texel word and a
+  //     per-lane register holding (table address | lane << 2), no add
+  //   [row info, kWalkWarps slices]  in the alignment gap in front of the table when it fits, else after it
+  //   [encode cell LUT, R interleaved replicas: cell i of replica r at word i*R + r]  after the table
+  const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_mem);
+  const uint32_t pad = (0x10000u - (smem0 & 0xFFFFu)) & 0xFFFFu;
+  float *s_lin = reinterpret_cast<float *>(s_mem + (pad >> 2));
+  constexpr int kRowWords = kWalkWarps * kWalkRowInfo;
+  const bool rows_in_gap = pad >= kRowWords * 4;
+  uint32_t *s_after = s_mem + (pad >> 2) + 256 * 64;
+  uint32_t *s_rows = rows_in_gap ? s_mem : s_after;
+  uint32_t *s_enc = s_after + (rows_in_gap ? 0 : kRowWords) + 4;
+  const int nenc = ((1 << p.enc_cells_log2) + 1) << ERL2;
+  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
+    s_lin[(i >> 5) * 64 + (i & 31)] = __ldg(&p.lin256[i >> 5]);
+    s_lin[(i >> 5) * 64 + 32 + (i & 31)] = __fmul_rn((float) (i >> 5), 1.0f / 255.0f);
+  }
+  for (int i = threadIdx.x; i < nenc; i += blockDim.x) s_enc[i] = __ldg(&p.enc_lut[i >> ERL2]);
+  // the encode-LUT address is (bits(2^23 + idx) << 2) + enc_base with the 2^23 folded into enc_base; it
+  // goes through shared memory so that ptxas sees an opaque register and emits a single LEA per lookup
+  if (threadIdx.x == 0) s_enc[-1] = (uint32_t) __cvta_generic_to_shared(s_enc) - (0x4B000000u << (2 + ERL2));
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const uint32_t lin_base = (uint32_t) __cvta_generic_to_shared(s_lin);  // warp-uniform
-  const uint32_t lane4 = lane << 2;
-  const uint32_t enc_base = (uint32_t) __cvta_generic_to_shared(s_enc) - (0x4B000000u << 2);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lin_lane = (smem0 + pad) | (lane << 2);  // bytes 3,2: table address; byte 0: lane * 4
+  const uint32_t rows_base = (uint32_t) __cvta_generic_to_shared(s_rows + warp * kWalkRowInfo);
+  const uint32_t enc_base = *reinterpret_cast<volatile uint32_t *>(s_enc - 1) + ((lane & ((1 << ERL2) - 1)) << 2);
   const float fN = (float) (1 << p.enc_cells_log2);
   const float clamp_lo = p.enc_clamp_lo;
-  const f32x2 one = pk(p.one, p.one), inv255_1 = pk(1.0f / 255.0f, 1.0f);
+  const f32x2 one = pk(p.one, p.one), neg1 = pk(-1.0f, -1.0f);
+  const f32x2 fN2 = pk(fN, fN), magic2 = pk(8388608.0f, 8388608.0f);
 
-  auto lin_of = [&](uint32_t px, int shift) -> float {
-    const uint32_t off = __byte_perm(px, lane4, shift == 16 ? 0x7724 : shift == 8 ? 0x7714 : 0x7704);
+  auto lin_of = [&](uint32_t px, uint32_t sel, int extra) -> float {
+    const uint32_t addr = __byte_perm(px, lin_lane, sel);  // table | byte << 8 | lane << 2
     float v;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(lin_base + off));
+    if (extra)
+      asm("ld.shared.f32 %0, [%1+128];" : "=f"(v) : "r"(addr));
+    else
+      asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
   };
-  auto texel = [&](uint32_t px) -> Lin4 {  // BGRA8 sRGB texel -> linear (R,G,B), A/255
+  auto texel = [&](uint32_t px) -> Lin4 {  // BGRA8 sRGB texel -> linear (R,G), (B, A/255)
     Lin4 t;
-    t.rg = pk(lin_of(px, 16), lin_of(px, 8));
-    const float a = __fadd_rn(__uint_as_float(__byte_perm(px, 0x4B000000u, 0x7543)), -8388608.0f);
-    t.ba = mul2(pk(lin_of(px, 0), a), pk(1.0f, 1.0f / 255.0f));
+    t.rg = pk(lin_of(px, 0x7624, 0), lin_of(px, 0x7614, 0));
+    t.ba = pk(lin_of(px, 0x7604, 0), lin_of(px, 0x7634, 1));
     return t;
   };
-  auto enc = [&](float v) -> uint32_t {  // linear -> sRGB code sum (byte 3)
-    float xc = fmaxf(v, clamp_lo), t;
-    asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(t) : "f"(xc), "f"(fN));
+  auto enc_idx = [&](float t) -> uint32_t {  // cell-LUT entry for the index held in the float 2^23 + idx
     uint32_t e;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((__float_as_uint(t) << 2) + enc_base));
-    return e + __float_as_uint(xc);
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((__float_as_uint(t) << (2 + ERL2)) + enc_base));
+    return e;
   };
 
-  const int tiles_x = (p.ow + 511) / 512, tiles_y = (p.oh + kRescaleTH - 1) / kRescaleTH;
+  const int tiles_x = (p.ow + 31) >> 5, tiles_y = (p.oh + kWalkTH - 1) / kWalkTH;
   const unsigned tiles_per_frame = tiles_x * tiles_y;
   const unsigned tiles = (unsigned) p.nframes * tiles_per_frame;
-  for (unsigned t = blockIdx.x; t < tiles; t += gridDim.x) {
+  const int ylast = p.ih - 1;
+  const unsigned pi = (unsigned) p.pi, po = (unsigned) p.po;
+  for (unsigned t = blockIdx.x * kWalkWarps + warp; t < tiles; t += gridDim.x * kWalkWarps) {
     const unsigned f = t / tiles_per_frame, tr = t - f * tiles_per_frame;
     const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
-    const int ox = tx * 512 + threadIdx.x;
-    if (ox >= p.ow) continue;
-    // horizontal sample position of this column: same float32 steps as oracle_rescale_bgra
+    const int oy0 = ty * kWalkTH;
+    // ---- row info of this tile: {fy, top source row (unclamped), output row}
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kWalkTH / 32; k++) {
+      const int r = k * 32 + lane, oy = oy0 + r;
+      const float sy = __fadd_rn(__fmul_rn(__fadd_rn((float) oy, 0.5f), p.scale_y), -0.5f);
+      const float fy0 = floorf(sy);
+      uint4 e;
+      e.x = __float_as_uint(__fsub_rn(sy, fy0));
+      e.y = oy < p.oh ? (uint32_t) (int) fy0 : 0x7fffffffu;
+      e.z = (unsigned) oy;
+      e.w = 0;
+      asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(rows_base + r * 16), "r"(e.x), "r"(e.y), "r"(e.z), "r"(e.w) : "memory");
+    }
+    if (lane == 0)
+      asm volatile("st.shared.v4.u32 [%0], {%1,%1,%1,%1};" ::"r"(rows_base + kWalkTH * 16), "r"(0x7fffffffu) : "memory");
+    __syncwarp();
+
+    // ---- horizontal sample position of this column: same float32 steps as oracle_rescale_bgra
+    const int ox = tx * 32 + lane;
+    const bool live = ox < p.ow;
     const float sx = __fadd_rn(__fmul_rn(__fadd_rn((float) ox, 0.5f), p.scale_x), -0.5f);
     const float fx0 = floorf(sx);
     const float fx = __fsub_rn(sx, fx0);
     const int xi = (int) fx0;
     const int x0 = min(max(xi, 0), p.iw - 1), x1 = min(max(xi + 1, 0), p.iw - 1);
-    const f32x2 fx2 = pk(fx, fx), neg1 = pk(-1.0f, -1.0f);
-    const uint32_t *src0 = reinterpret_cast<const uint32_t *>(p.in + (long long) f * p.si) + x0;
-    const uint32_t *src1 = reinterpret_cast<const uint32_t *>(p.in + (long long) f * p.si) + x1;
-    uint8_t *dst = p.out + (long long) f * p.so + (long long) ox * 4;
-    const unsigned pi4 = (unsigned) (p.pi >> 2), po = (unsigned) p.po;
+    const f32x2 fx2 = pk(fx, fx);
+    const uint8_t *src0 = p.in + (long long) f * p.si + (size_t) x0 * 4;
+    uint8_t *dp = p.out + (long long) f * p.so + (size_t) min(ox, p.ow - 1) * 4 + (size_t) oy0 * po;
+
     auto blend = [&](uint32_t w0, uint32_t w1) -> Lin4 {  // top/bot of the oracle: t0 + fx * (t1 - t0)
       const Lin4 t0 = texel(w0), t1 = texel(w1);
       Lin4 h;
@@ -146,72 +199,88 @@ __global__ void __launch_bounds__(512, 2) k_rescale_cols(const RescaleArgs p) {
       h.ba = fma2_rn(mul2(fx2, fma2_rn(t0.ba, neg1, t1.ba)), one, t0.ba);
       return h;
     };
-    const int ylast = p.ih - 1;
-    auto fetch = [&](int y, uint32_t &w0, uint32_t &w1) {  // taps of source row min(y, ih-1)
-      const size_t o = (size_t) ((unsigned) min(y, ylast) * pi4);
-      w0 = __ldg(src0 + o);
-      w1 = __ldg(src1 + o);
+    // taps of the next source row; the fetch pointer stops advancing at the last row (clamp to edge)
+    // (two pointers: x1 - x0 is 0 at the clamped image edges and 1 elsewhere, a per-thread quantity)
+    const uint8_t *fp0 = nullptr, *fp1 = nullptr;
+    // loads the taps of source row clamp(row, 0, ih - 1), which is where the pointers stand, and steps
+    // them down unless the next row clamps to the same one
+    auto fetch = [&](int row, uint32_t &w0, uint32_t &w1) {
+      w0 = __ldg(reinterpret_cast<const uint32_t *>(fp0));
+      w1 = __ldg(reinterpret_cast<const uint32_t *>(fp1));
+      const unsigned inc = (unsigned) row < (unsigned) ylast ? pi : 0u;  // also 0 for row == -1
+      fp0 += inc;
+      fp1 += inc;
     };
-    auto emit = [&](int oy, float fy, const Lin4 &A, const Lin4 &B) {
-      // v = top + fy * (bot - top), clamp01 (the saturating add), per channel
+    auto emit = [&](float fy, const Lin4 &A, const Lin4 &B) {
+      // v = top + fy * (bot - top) per channel; clamp01 is the identity here (see above)
       const f32x2 fy2 = pk(fy, fy);
-      float prg0, prg1, pba0, pba1, a0, a1, a2, a3;
-      upk(mul2(fy2, fma2_rn(A.rg, neg1, B.rg)), prg0, prg1);
-      upk(mul2(fy2, fma2_rn(A.ba, neg1, B.ba)), pba0, pba1);
-      upk(A.rg, a0, a1); upk(A.ba, a2, a3);
-      const uint32_t sr = enc(add_sat(a0, prg0)), sg = enc(add_sat(a1, prg1)), sb = enc(add_sat(a2, pba0));
-      const uint32_t ac = (uint32_t) round_pos(__fmul_rn(add_sat(a3, pba1), 255.0f));
+      const f32x2 vrg = fma2_rn(mul2(fy2, fma2_rn(A.rg, neg1, B.rg)), one, A.rg);
+      const f32x2 vba = fma2_rn(mul2(fy2, fma2_rn(A.ba, neg1, B.ba)), one, A.ba);
+      float vr, vg, vb, va, tr_, tg_, tb_;
+      upk(vrg, vr, vg);
+      upk(vba, vb, va);
+      vr = fmaxf(vr, clamp_lo); vg = fmaxf(vg, clamp_lo); vb = fmaxf(vb, clamp_lo);
+      upk(fma2_rz(pk(vr, vg), fN2, magic2), tr_, tg_);
+      asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(tb_) : "f"(vb), "f"(fN));
+      const uint32_t sr = enc_idx(tr_) + __float_as_uint(vr);  // byte 3 = sRGB code
+      const uint32_t sg = enc_idx(tg_) + __float_as_uint(vg);
+      const uint32_t sb = enc_idx(tb_) + __float_as_uint(vb);
+      // alpha: round(va * 255), half away from zero: the integer part of RZ(x + 32768.5) sits in byte 1
+      float ta;
+      asm("add.rz.f32 %0, %1, 0f47000080;" : "=f"(ta) : "f"(__fmul_rn(va, 255.0f)));
       const uint32_t bg = __byte_perm(sb, sg, 0x0073);
-      const uint32_t w = __byte_perm(bg, __byte_perm(sr, ac, 0x0043), 0x5410);
-      *reinterpret_cast<uint32_t *>(dst + (size_t) ((unsigned) oy * po)) = w;
+      const uint32_t w = __byte_perm(bg, __byte_perm(sr, __float_as_uint(ta), 0x0053), 0x5410);
+      if (live) *reinterpret_cast<uint32_t *>(dp) = w;
+      dp += po;
     };
-    // Walk the source rows this strip needs (they are consecutive for scale <= 1).  A = blended row
-    // y, B = blended row y + 1; every output row whose top tap is y is emitted from (A, B).  The raw
-    // taps of the next kPD rows sit in registers, fetched kPD rows ahead of use (one DRAM round trip
-    // per source row per warp otherwise bounds the kernel: measured 196 Gpix/s out, issue 78 % idle
-    // on the first use of the loaded texels).
-    constexpr int kPD = 3;
-    int oy = ty * kRescaleTH;
-    const int oy1 = min(oy + kRescaleTH, p.oh);
-    float oyf = (float) oy;
-    float sy = __fadd_rn(__fmul_rn(__fadd_rn(oyf, 0.5f), p.scale_y), -0.5f);
-    float fy0 = floorf(sy);
-    int y = min(max((int) fy0, 0), ylast);  // first top row
-    uint32_t q0[kPD], q1[kPD], a0w, a1w;
+
+    // ---- walk.  H[j & 1] = blended row y, H[(j + 1) & 1] = blended row y + 1; the raw taps of the
+    // next kWalkPD rows sit in registers, fetched that many rows ahead of use.
+    uint32_t ip = rows_base;  // row-info cursor
+    uint4 info;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(info.x), "=r"(info.y), "=r"(info.z), "=r"(info.w) : "r"(ip));
+    int y = (int) info.y;     // first top row, >= -1
+    uint32_t q0[kWalkPD], q1[kWalkPD], a0w, a1w;
+    fp0 = ptr_mad(src0, (unsigned) max(y, 0), pi);
+    fp1 = fp0 + (x1 - x0) * 4;
     fetch(y, a0w, a1w);
 #pragma unroll
-    for (int j = 0; j < kPD; j++) fetch(y + 1 + j, q0[j], q1[j]);
-    Lin4 A = blend(a0w, a1w);
-    while (oy < oy1) {  // every condition below depends on oy only: warp-uniform
+    for (int j = 0; j < kWalkPD; j++) fetch(y + 1 + j, q0[j], q1[j]);
+    Lin4 H[2];
+    H[0] = blend(a0w, a1w);
+    bool done = false;
+    while (!done) {  // every condition below is warp-uniform
 #pragma unroll
-      for (int j = 0; j < kPD; j++) {
-        const Lin4 B = blend(q0[j], q1[j]);   // row min(y + 1, ih - 1); equals A bit for bit at the bottom edge
-        fetch(y + 1 + kPD, q0[j], q1[j]);     // refill this slot with the row kPD further down
-        while (oy < oy1) {                    // emit the output rows whose clamped top tap is y
-          const int yi = (int) fy0;
-          if (min(max(yi, 0), ylast) != y) break;
-          // at the clamped image edges both taps are the same row and the blend degenerates to it
-          const bool edge = min(max(yi + 1, 0), ylast) == y;
-          emit(oy, __fsub_rn(sy, fy0), A, edge ? A : B);
-          oy++;
-          oyf += 1.0f;
-          sy = __fadd_rn(__fmul_rn(__fadd_rn(oyf, 0.5f), p.scale_y), -0.5f);
-          fy0 = floorf(sy);
+      for (int j = 0; j < 2 * kWalkPD; j++) {
+        H[(j + 1) & 1] = blend(q0[j % kWalkPD], q1[j % kWalkPD]);                 // row min(y + 1, ih - 1)
+        fetch(y + 1 + kWalkPD, q0[j % kWalkPD], q1[j % kWalkPD]);                 // refill the slot
+        while ((int) info.y <= y) {  // emit the output rows whose top tap is y (<=: can never spin)
+          emit(__uint_as_float(info.x), H[j & 1], H[(j + 1) & 1]);
+          ip += 16;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(info.x), "=r"(info.y), "=r"(info.z), "=r"(info.w) : "r"(ip));
         }
-        A = B;
-        y = min(y + 1, ylast);
-        if (oy >= oy1) break;
+        y++;
+        if (info.y == 0x7fffffffu) { done = true; break; }
       }
     }
   }
 }
 
+static size_t walk_smem_bytes(int enc_cells_log2, int rep_log2) {  // 64 KB of alignment slack in front of the table
+  return 65536 + (256 * 64 + (size_t) kWalkWarps * kWalkRowInfo + 4 + ((((size_t) 1 << enc_cells_log2) + 1) << rep_log2)) * 4;
+}
+
 int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
-  if (a.iw <= a.ow && a.ih <= a.oh && a.enc_cells_log2 <= 13) {  // upscale or same size: column walker
-    const size_t smem2 = (256 * 64 + (size_t) (1 << a.enc_cells_log2) + 1) * 4;
-    const long long tiles2 = (long long) a.nframes * ((a.ow + 511) / 512) * ((a.oh + kRescaleTH - 1) / kRescaleTH);
-    long long grid2 = tiles2 < (long long) sm_count * 2 ? tiles2 : (long long) sm_count * 2;
-    k_rescale_cols<<<(unsigned) grid2, 512, smem2, (cudaStream_t) stream>>>(a);
+  // upscale or same size, and every output-row byte offset fits 32 bits: column walker
+  if (a.iw <= a.ow && a.ih <= a.oh && a.enc_cells_log2 <= 13 && (long long) a.oh * a.po < (1ll << 32) &&
+      (long long) a.ih * a.pi < (1ll << 32) && a.pi >= 0 && a.po >= 0) {
+    const long long tiles2 = (long long) a.nframes * ((a.ow + 31) / 32) * ((a.oh + kWalkTH - 1) / kWalkTH);
+    const long long ctas = (tiles2 + kWalkWarps - 1) / kWalkWarps;
+    long long grid2 = ctas < (long long) sm_count ? ctas : (long long) sm_count;
+    if (walk_smem_bytes(a.enc_cells_log2, 2) <= kMaxDynSmem)
+      k_rescale_cols<2><<<(unsigned) grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(a);
+    else
+      k_rescale_cols<0><<<(unsigned) grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 0), (cudaStream_t) stream>>>(a);
     return (int) cudaGetLastError();
   }
   const size_t smem = (256 + (size_t) (1 << a.enc_cells_log2) + 1) * 4;
@@ -222,7 +291,9 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
 }
 
 int rescale_kernels_init() {
-  return (int) cudaFuncSetAttribute(k_rescale_cols, cudaFuncAttributeMaxDynamicSharedMemorySize, (256 * 64 + 8193) * 4);
+  int e = (int) cudaFuncSetAttribute(k_rescale_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  return (int) cudaFuncSetAttribute(k_rescale_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) walk_smem_bytes(13, 0));
 }
 
 }  // namespace bt709
