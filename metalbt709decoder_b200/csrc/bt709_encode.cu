@@ -104,15 +104,15 @@ __global__ void __launch_bounds__(256) k_encode(const EncodeArgs p) {
 //   * both 256-entry byte tables are merged into one {linear, requantised/255} float2 table with one
 //     8-byte replica per lane (entry stride 256 B), so the LDS.64 gathers are conflict-free and the
 //     address (byte << 8) | (lane << 3) is a single PRMT of the pixel word and the lane register;
-//   * float32 steps run two at a time on the packed FADD2/FMUL2/FFMA2 pipe.  ptxas contracts a
-//     packed multiply feeding a packed add into one FFMA2 (one rounding instead of two), so every
-//     add that follows a multiply is written fma(product, one, addend) with a run-time 1.0;
+//   * the chroma steps of the lane's two blocks run two at a time on the packed FADD2/FMUL2/FFMA2 pipe.
+//     ptxas contracts a packed multiply feeding a packed add into one FFMA2 (one rounding instead of
+//     two), so every add that follows a multiply is written fma(product, one, addend) with a run-time 1.0;
 //   * x / 1.8556f and x / 1.5748f are q0 = x*rc; r = fma(-q0, c, x); q = fma(r, rc, q0), which equals
 //     the IEEE quotient for every value this path can produce (all 2^24 8-bit RGB triples checked
 //     on the host: tests/test_tables_cpu.py) and costs 3 instructions instead of ~10;
-//   * round() of the positive results is add.rz(+0.5) then add.rz(+2^23): the code is the low byte.
+//   * round() of the positive results is one add.rz(+32768.5): the code is byte 1 of the float.
 struct EncK {
-  f32x2 one, kr, kg, kb, s219, o16, s224, o128, rcb, ncb, rcr, ncr, quarter, half, magic, inv255, nmagic;
+  f32x2 one, kr, kg, kb, s224, o128, rcb, ncb, rcr, ncr, quarter, rnd, inv255, nmagic;
 };
 
 __device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) {
@@ -122,13 +122,6 @@ __device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) {
 }
 // exact a + b where a (or b) may be the result of a packed multiply: never contracted
 __device__ __forceinline__ f32x2 add2_nc(f32x2 a, f32x2 b, const EncK &k) { return fma2_rn(a, k.one, b); }
-
-// Ey of BT709.h:223 for two pixels, then round(Ey*219 + 16) (BT709.h:234, 245): magic floats 2^23 + Y
-__device__ __forceinline__ f32x2 enc_luma2(f32x2 rn, f32x2 gn, f32x2 bn, const EncK &k) {
-  f32x2 ey = add2_nc(add2_nc(mul2(k.kr, rn), mul2(k.kg, gn), k), mul2(k.kb, bn), k);
-  f32x2 ay = add2_nc(mul2(ey, k.s219), k.o16, k);
-  return add2_rz(add2_rz(ay, k.half), k.magic);
-}
 
 template <bool WRAP>
 __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
@@ -156,9 +149,9 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   EncK k;
   auto bc = [](float v) { return pk(v, v); };
   k.one = bc(p.one); k.kr = bc(0.2126f); k.kg = bc(0.7152f); k.kb = bc(0.0722f);
-  k.s219 = bc(219.0f); k.o16 = bc(16.0f); k.s224 = bc(224.0f); k.o128 = bc(128.0f);
+  k.s224 = bc(224.0f); k.o128 = bc(128.0f);
   k.rcb = bc(1.0f / 1.8556f); k.ncb = bc(-1.8556f); k.rcr = bc(1.0f / 1.5748f); k.ncr = bc(-1.5748f);
-  k.quarter = bc(0.25f); k.half = bc(0.5f); k.magic = bc(8388608.0f); k.nmagic = bc(-8388608.0f);
+  k.quarter = bc(0.25f); k.rnd = bc(32768.5f); k.nmagic = bc(-8388608.0f);
   k.inv255 = bc(1.0f / 255.0f);
 
   const unsigned r_local = warp / p.tiles_per_row;
@@ -206,39 +199,39 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
       na = ld_stream_u128(ptr_mad(p.in, oi, 16));
       nb = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
     }
-    // Walk the four pixel pairs in the order NW, NE (row 0), SW, SE (row 1): pair (0,2) holds the
-    // west pixels of blocks A and B, pair (1,3) the east pixels.  Luma is finished per pair; the
+    // Per pixel: three LDS.64 {linear, requantised/255}; the luma runs on scalar float ops straight
+    // from the loaded registers (packing two pixels into f32x2 pairs cost two MOVs per pair because
+    // an LDS.64 dictates where its results land: 23 % of the loop was register moves).  The
     // linear-light sums accumulate in the reference's order ((NW + NE) + SW) + SE (BT709.h:1182-1183).
     uint32_t yw[2];
-    f32x2 sum[3];
+    float sum[2][3] = {};  // [block A/B][R,G,B]
+#pragma unroll 1
+    for (int r = 0; r < 2; r++) {  // a real loop: unrolled, the 24 hoisted LDS.64 results spill the loop state
+      float ty[4];
+      const uint4 row = r ? b : a;
 #pragma unroll
-    for (int r = 0; r < 2; r++) {
-      const uint32_t p0 = r ? b.x : a.x, p1 = r ? b.y : a.y, p2 = r ? b.z : a.z, p3 = r ? b.w : a.w;
-      f32x2 m[2];
+      for (int i = 0; i < 4; i++) {
+        const uint32_t px = i == 0 ? row.x : i == 1 ? row.y : i == 2 ? row.z : row.w;
+        float l[3], c[3];
+        fetch(px, 16, l[0], c[0]); fetch(px, 8, l[1], c[1]); fetch(px, 0, l[2], c[2]);
+        // Ey of BT709.h:223, then round(Ey*219 + 16) (BT709.h:234, 245): the integer part of
+        // RZ(x + 32768.5) sits in byte 1 of the float
+        const float ey = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, c[0]), __fmul_rn(0.7152f, c[1])), __fmul_rn(0.0722f, c[2]));
+        asm("add.rz.f32 %0, %1, 0f47000080;" : "=f"(ty[i]) : "f"(__fadd_rn(__fmul_rn(ey, 219.0f), 16.0f)));
 #pragma unroll
-      for (int e = 0; e < 2; e++) {  // e = 0: pixels (0,2); e = 1: pixels (1,3)
-        const uint32_t pw = e ? p1 : p0, pe = e ? p3 : p2;
-        float lw[3], cw_[3], le[3], ce[3];
-        fetch(pw, 16, lw[0], cw_[0]); fetch(pw, 8, lw[1], cw_[1]); fetch(pw, 0, lw[2], cw_[2]);
-        fetch(pe, 16, le[0], ce[0]); fetch(pe, 8, le[1], ce[1]); fetch(pe, 0, le[2], ce[2]);
-        m[e] = enc_luma2(pk(cw_[0], ce[0]), pk(cw_[1], ce[1]), pk(cw_[2], ce[2]), k);
-#pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-          const f32x2 v = pk(lw[ch], le[ch]);
-          sum[ch] = (r == 0 && e == 0) ? v : add2(sum[ch], v);
-        }
+        for (int ch = 0; ch < 3; ch++)
+          sum[i >> 1][ch] = (i & 1) == 0 ? (r == 0 ? l[ch] : __fadd_rn(sum[i >> 1][ch], l[ch])) : __fadd_rn(sum[i >> 1][ch], l[ch]);
       }
-      uint32_t y0, y1, y2, y3;
-      upku(m[0], y0, y2); upku(m[1], y1, y3);
-      yw[r] = __byte_perm(__byte_perm(y0, y1, 0x0040), __byte_perm(y2, y3, 0x0040), 0x5410);
+      yw[r] = __byte_perm(__byte_perm(__float_as_uint(ty[0]), __float_as_uint(ty[1]), 0x0051),
+                          __byte_perm(__float_as_uint(ty[2]), __float_as_uint(ty[3]), 0x0051), 0x5410);
     }
-    // ---- chroma of blocks A and B: mean, requantise to 8 bits in the output gamma
+    // ---- chroma of blocks A and B (packed A|B): mean, requantise to 8 bits in the output gamma
     // (BT709.h:1418-1420), back to unorm (sRGB.h:32-36)
     f32x2 q[3];
 #pragma unroll
     for (int ch = 0; ch < 3; ch++) {
       float mA, mB;
-      upk(mul2(sum[ch], k.quarter), mA, mB);
+      upk(mul2(pk(sum[0][ch], sum[1][ch]), k.quarter), mA, mB);
       q[ch] = mul2(add2(pk(code_of(mA), code_of(mB)), k.nmagic), k.inv255);
     }
     f32x2 ey = add2_nc(add2_nc(mul2(k.kr, q[0]), mul2(k.kg, q[1]), k), mul2(k.kb, q[2]), k);
@@ -246,11 +239,11 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
     f32x2 qb = mul2(xb, k.rcb), qr = mul2(xr, k.rcr);
     qb = fma2_rn(fma2_rn(qb, k.ncb, xb), k.rcb, qb);
     qr = fma2_rn(fma2_rn(qr, k.ncr, xr), k.rcr, qr);
-    f32x2 mb = add2_rz(add2_rz(add2_nc(mul2(qb, k.s224), k.o128, k), k.half), k.magic);
-    f32x2 mr = add2_rz(add2_rz(add2_nc(mul2(qr, k.s224), k.o128, k), k.half), k.magic);
+    f32x2 mb = add2_rz(add2_nc(mul2(qb, k.s224), k.o128, k), k.rnd);
+    f32x2 mr = add2_rz(add2_nc(mul2(qr, k.s224), k.o128, k), k.rnd);
     uint32_t cbA, cbB, crA, crB;
     upku(mb, cbA, cbB); upku(mr, crA, crB);
-    const uint32_t cw = __byte_perm(__byte_perm(cbA, crA, 0x0040), __byte_perm(cbB, crB, 0x0040), 0x5410);
+    const uint32_t cw = __byte_perm(__byte_perm(cbA, crA, 0x0051), __byte_perm(cbB, crB, 0x0051), 0x5410);
     st_stream_u32((void *) ptr_mad(p.y, oy, 4), yw[0]);
     st_stream_u32((void *) ptr_mad(p.y, oy + p.py4, 4), yw[1]);
     st_stream_u32((void *) ptr_mad(p.c, oc, 4), cw);
