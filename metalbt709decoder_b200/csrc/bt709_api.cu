@@ -28,6 +28,11 @@ struct bt709_ctx {
   const uint32_t *dec_lut[4] = {};
   float dec_clamp[4] = {};
   int dec_cells[4] = {};
+  // log-cell form of the Linear-mode step function (conflict-free when replicated per lane)
+  const uint32_t *dec_log_lut = nullptr;
+  float dec_log_clamp = 0.f;
+  int dec_log_cells = 0;
+  unsigned dec_log_first = 0;
   // BT709_from_linear: linear float -> byte in gamma g (g = APPLE, SRGB, LINEAR)
   const uint32_t *fl_lut[3] = {};
   float fl_clamp[3] = {};
@@ -113,7 +118,7 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
 
   // ---- build every table on the host, once
   BlobBuilder blob;
-  size_t off_dec[4], off_fl[3], off_lin[3], off_comp[3][3], off_e444;
+  size_t off_dec[4], off_fl[3], off_lin[3], off_comp[3][3], off_e444, off_log = 0;
   for (int g = 0; g < 4; g++) {
     StepFn fn;
     CellLut lut;
@@ -126,6 +131,13 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
     ctx->dec_clamp[g] = lut.clamp_lo;
     ctx->dec_cells[g] = n;
     off_dec[g] = blob.add(lut.entries.data(), lut.entries.size());
+    LogLut llut;
+    if (g == kLinear && build_log_lut(fn, &llut)) {  // optional: the uniform table above stays the fallback
+      ctx->dec_log_clamp = llut.clamp_lo;
+      ctx->dec_log_cells = (int) llut.entries.size();
+      ctx->dec_log_first = llut.first;
+      off_log = blob.add(llut.entries.data(), llut.entries.size());
+    }
   }
   for (int g = 0; g < 3; g++) {
     StepFn fn;
@@ -160,6 +172,7 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
   }
   const uint32_t *base = (const uint32_t *) ctx->dev_blob;
   for (int g = 0; g < 4; g++) ctx->dec_lut[g] = base + off_dec[g];
+  if (ctx->dec_log_cells) ctx->dec_log_lut = base + off_log;
   for (int g = 0; g < 3; g++) {
     ctx->fl_lut[g] = base + off_fl[g];
     ctx->lin256[g] = (const float *) (base + off_lin[g]);
@@ -228,6 +241,10 @@ int bt709_decode_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane
   if (alpha_y) { a.a = (const uint8_t *) alpha_y->ptr; a.pa = (long long) alpha_y->pitch; a.sa = (long long) alpha_y->frame_stride; }
   a.w = w; a.h = h; a.nframes = nframes;
   a.lut = ctx->dec_lut[gamma]; a.clamp_lo = ctx->dec_clamp[gamma]; a.cells_log2 = ctx->dec_cells[gamma];
+  if ((int) gamma == (int) kLinear && ctx->dec_log_lut) {
+    a.log_lut = ctx->dec_log_lut; a.log_clamp_lo = ctx->dec_log_clamp;
+    a.log_cells = ctx->dec_log_cells; a.log_first = ctx->dec_log_first;
+  }
   a.m = ctx->m;
   a.one = 1.0f;
   return finish(ctx, launch_decode(a, ctx->sm_count, stream), stream, wait);

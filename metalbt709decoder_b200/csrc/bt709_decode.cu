@@ -39,7 +39,13 @@ __device__ __forceinline__ void lut2(float xa, float xb, float clamp_lo, const D
                                      uint32_t &sa, uint32_t &sb) {
   float ca = fmaxf(xa, clamp_lo), cb = fmaxf(xb, clamp_lo);
   uint32_t ta, tb;
-  upku(fma2_rz(pk(ca, cb), k.fN, k.magic), ta, tb);
+  if (CL2 == 0) {  // log-spaced cells: the index is the upper half of the float (sign, exponent, 7 mantissa bits)
+    // PRMT, not a shift: ptxas merges (x >> 16) << 7 into SHF + LOP3 + IADD, this stays PRMT + LEA
+    ta = __byte_perm(__float_as_uint(ca), 0, 0x4432);
+    tb = __byte_perm(__float_as_uint(cb), 0, 0x4432);
+  } else {
+    upku(fma2_rz(pk(ca, cb), k.fN, k.magic), ta, tb);
+  }
   uint32_t ea, eb;
   asm("ld.shared.u32 %0, [%1];" : "=r"(ea) : "r"((ta << (2 + RL2)) + sbase));
   asm("ld.shared.u32 %0, [%1];" : "=r"(eb) : "r"((tb << (2 + RL2)) + sbase));
@@ -148,13 +154,15 @@ template <int CL2, int RL2, bool ALPHA, bool FULL, bool WRAP, int PD, int THREAD
 __global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) {
   extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = 1 << CL2, R = 1 << RL2;
-  for (int i = threadIdx.x; i < (N + 1) * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  const int entries = CL2 ? N + 1 : p.log_cells;  // CL2 == 0: log-spaced cell LUT (bt709_tables.h: LogLut)
+  for (int i = threadIdx.x; i < entries * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
+  // the index register holds 2^23 + cell (uniform cells) or first + cell (log cells): fold the bias in
   const uint32_t sbase = (uint32_t) __cvta_generic_to_shared(s_lut) + ((lane & (R - 1)) << 2) -
-                         (0x4B000000u << (2 + RL2));
+                         ((CL2 ? 0x4B000000u : p.log_first) << (2 + RL2));
   const float clamp_lo = p.clamp_lo;
   DecodeK2 k;
   k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
@@ -241,15 +249,16 @@ template <int CL2, int RL2, bool ALPHA, bool WRAP, int D, int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) {
   extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = 1 << CL2, R = 1 << RL2;
-  constexpr uint32_t kLutBytes = (uint32_t) (N + 1) * R * 4;
+  const int entries = CL2 ? N + 1 : p.log_cells;  // CL2 == 0: log-spaced cell LUT
+  const uint32_t kLutBytes = (uint32_t) entries * R * 4;
   constexpr uint32_t kStage = ALPHA ? 640 : 384;  // Y0 | Y1 | CbCr (| A0 | A1), 128 B each
-  for (int i = threadIdx.x; i < (N + 1) * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  for (int i = threadIdx.x; i < entries * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
   const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_lut);
-  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - (0x4B000000u << (2 + RL2));
+  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - ((CL2 ? 0x4B000000u : p.log_first) << (2 + RL2));
   const uint32_t ring = smem0 + kLutBytes + warp * (D * kStage);
   const float clamp_lo = p.clamp_lo;
   DecodeK2 k;
@@ -555,12 +564,16 @@ constexpr int kRingDepth = BT709_RING_DEPTH;  // stages of the per-warp cp.async
 
 template <int CL2, int RL2, bool ALPHA, bool FULL, bool WRAP>
 static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
-  constexpr size_t smem = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
+  const size_t smem = (size_t) (CL2 ? (1 << CL2) + 1 : a0.log_cells) * (1 << RL2) * 4;
   auto k = k_decode_fast<CL2, RL2, ALPHA, FULL, WRAP, kPrefetchDepth, kDecodeThreads>;
   auto kring = k_decode_ring<CL2, RL2, ALPHA, WRAP, kRingDepth, kDecodeThreads>;
-  constexpr size_t smem_ring = smem + (size_t) (kDecodeThreads / 32) * kRingDepth * (ALPHA ? 640 : 384);
+  // ring slices exist for the warps that have a tile only.  The fully replicated log-cell LUT (209 KB)
+  // leaves room for 30 of them (1920 or 3840 wide, no alpha); otherwise that mode prefetches in registers
+  const int wpc = kDecodeThreads / 32;
+  const int active_warps = a0.tiles_per_row >= wpc ? wpc : a0.tiles_per_row * a0.rps;
+  const size_t smem_ring = smem + (size_t) active_warps * kRingDepth * (ALPHA ? 640 : 384);
   static const bool no_ring = getenv("BT709_NO_RING") != nullptr;
-  const bool use_ring = FULL && !no_ring && aligned(a0.y, 16) && aligned(a0.py, 16) && aligned(a0.sy, 16) &&
+  const bool use_ring = smem_ring <= kMaxDynSmem && FULL && !no_ring && aligned(a0.y, 16) && aligned(a0.py, 16) && aligned(a0.sy, 16) &&
                         aligned(a0.c, 16) && aligned(a0.pc, 16) && aligned(a0.sc, 16) &&
                         (!ALPHA || (aligned(a0.a, 16) && aligned(a0.pa, 16) && aligned(a0.sa, 16)));
   // frames per launch such that every 32-bit unit offset stays below 2^32
@@ -660,6 +673,7 @@ static int launch_decode_fast(const DecodeArgs &a0, int sm_count, cudaStream_t s
   // per-thread loads (774 vs 811 Gpix/s on 600 x 1080p): the path is bound by HBM *write*
   // bandwidth (profiles/r01_membw_probe.json), not by read latency.  Opt-in for reproduction.
   static const bool use_bulk = getenv("BT709_BULK") != nullptr;
+  if constexpr (CL2 != 0)
   if (use_bulk && bulk_ok<CL2, RL2, ALPHA>(a, &nstages, &stage_bytes, &nrows)) {
     constexpr size_t lut = (size_t) ((1 << CL2) + 1) * (1 << RL2) * 4;
     a.nstages = nstages; a.stage_bytes = stage_bytes; a.nrows = nrows;
@@ -722,6 +736,13 @@ int launch_decode(const DecodeArgs &a0, int sm_count, void *stream) {
               (a.cells_log2 == 10 || a.cells_log2 == 12);
   if (alpha) fast = fast && aligned(a.a, 4) && aligned(a.pa, 4) && aligned(a.sa, 4);
   if (fast) {
+    // Linear mode: the steep pure-sRGB-encode step function needs 4096 uniform cells (8 replicas, 2-3 way
+    // bank conflicts) but only ~1650 log-spaced ones, which fit shared memory with one replica per lane
+    if (a.log_lut && a.log_cells > 0 && (size_t) a.log_cells * 128 <= kMaxDynSmem) {
+      a.lut = a.log_lut;
+      a.clamp_lo = a.log_clamp_lo;
+      return alpha ? launch_decode_fast<0, 5, true>(a, sm_count, s) : launch_decode_fast<0, 5, false>(a, sm_count, s);
+    }
     if (a.cells_log2 == 10)
       return alpha ? launch_decode_fast<10, 5, true>(a, sm_count, s) : launch_decode_fast<10, 5, false>(a, sm_count, s);
     return alpha ? launch_decode_fast<12, 3, true>(a, sm_count, s) : launch_decode_fast<12, 3, false>(a, sm_count, s);
@@ -734,6 +755,24 @@ int launch_decode(const DecodeArgs &a0, int sm_count, void *stream) {
   else
     k_decode_generic<false><<<(unsigned) grid, 256, 0, s>>>(a);
   return (int) cudaGetLastError();
+}
+
+template <bool ALPHA>
+static int optin_decode_smem_log() {
+  int e = (int) cudaFuncSetAttribute(k_decode_fast<0, 5, ALPHA, true, true, kPrefetchDepth, kDecodeThreads>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_fast<0, 5, ALPHA, true, false, kPrefetchDepth, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_fast<0, 5, ALPHA, false, true, kPrefetchDepth, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_ring<0, 5, ALPHA, true, kRingDepth, kDecodeThreads>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  return (int) cudaFuncSetAttribute(k_decode_ring<0, 5, ALPHA, false, kRingDepth, kDecodeThreads>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
 }
 
 template <int CL2, int RL2, bool ALPHA>
@@ -766,6 +805,8 @@ int decode_kernels_init() {
   if ((e = optin_decode_smem<10, 5, true>())) return e;
   if ((e = optin_decode_smem<12, 3, false>())) return e;
   if ((e = optin_decode_smem<12, 3, true>())) return e;
+  if ((e = optin_decode_smem_log<false>())) return e;
+  if ((e = optin_decode_smem_log<true>())) return e;
   return 0;
 }
 

@@ -28,6 +28,11 @@ struct DecodeArgs {
   const uint32_t *lut;  // cell LUT of the selected gamma, N + 1 words, device memory
   float clamp_lo;
   int cells_log2;
+  // optional log-spaced cell LUT of the same step function (bt709_tables.h: LogLut); nullptr = none
+  const uint32_t *log_lut;
+  float log_clamp_lo;
+  int log_cells;
+  unsigned log_first;
   MatrixConsts m;
   float one;  // 1.0f, deliberately a runtime value (see decode_row)
 };

@@ -172,6 +172,30 @@ bool build_cell_lut(const StepFn &fn, int cells_log2, CellLut *out) {
   return true;
 }
 
+bool build_log_lut(const StepFn &fn, LogLut *out) {
+  const uint32_t kOneHi = 0x3F800000u >> 16;
+  if (!(fn.thr[1] > 0.0f) || fn.thr[1] > 1.0f) return false;
+  const uint32_t first = f2u(fn.thr[1]) >> 16;  // the cell that holds (or starts at) the first threshold
+  out->first = first;
+  out->clamp_lo = u2f(first << 16);
+  out->entries.assign(kOneHi - first + 1, 0u);
+  for (uint32_t c = first; c <= kOneHi; c++) {
+    const uint32_t lo = c << 16, hi = lo + 0xFFFFu;  // bit patterns of the cell's first and last float
+    const uint32_t base = (uint32_t) fn.eval(u2f(lo));
+    const int cnt = fn.eval(u2f(hi)) - (int) base;
+    if (cnt > 1) return false;
+    // bits of the threshold inside the cell; if there is none, one past the cell (never reached)
+    const uint32_t tb = cnt == 1 ? f2u(fn.thr[base + 1]) : lo + 0x10000u;
+    out->entries[c - first] = (base << 24) + (1u << 24) - tb;
+  }
+  return true;
+}
+
+int log_lut_eval(const LogLut &lut, float x) {
+  float xc = x > lut.clamp_lo ? x : lut.clamp_lo;
+  return (int) ((lut.entries[(f2u(xc) >> 16) - lut.first] + f2u(xc)) >> 24);
+}
+
 int build_cell_lut_auto(const StepFn &fn, int lo, int hi, CellLut *out) {
   for (int n = lo; n <= hi; n++)
     if (build_cell_lut(fn, n, out)) return n;
@@ -219,6 +243,9 @@ int selftest_host() {
     CellLut lut;
     if (!build_step_fn(decode_code, g, &fn)) return 1;
     if (!build_cell_lut(fn, g == kLinear ? 12 : 10, &lut)) return 2;
+    LogLut llut;  // the Linear mode's fast path uses the log-cell form of the same step function
+    const bool has_log = g == kLinear;
+    if (has_log && !build_log_lut(fn, &llut)) return 9;
     std::atomic<long> bad(0);
     std::vector<std::thread> th;
     for (int t = 0; t < 8; t++)
@@ -231,7 +258,9 @@ int selftest_host() {
             for (int Cr = 0; Cr < 256; Cr++) {
               float x = (yt + cbg) + ((Cr - 128) * m.inv255) * m.g_cr;
               x = x < 0.f ? 0.f : (x > 1.f ? 1.f : x);
-              if (cell_lut_eval(lut, x) != decode_code(g, x)) b++;
+              const int want = decode_code(g, x);
+              if (cell_lut_eval(lut, x) != want) b++;
+              if (has_log && log_lut_eval(llut, x) != want) b++;
             }
           }
         }

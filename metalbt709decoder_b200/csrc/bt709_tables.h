@@ -60,6 +60,22 @@ int build_cell_lut_auto(const StepFn &fn, int lo, int hi, CellLut *out);
 // Host model of the device lookup (bit-for-bit what the kernels do).
 int cell_lut_eval(const CellLut &lut, float x);
 
+// ---- log-cell LUT ----------------------------------------------------------------------
+// Same step function, cells spaced like the float32 format itself: cell = bits(x) >> 16 (sign,
+// exponent and 7 mantissa bits), first cell = the one clamp_lo starts.  A steep curve such as the
+// pure sRGB encode of the decoder's Linear mode needs 4096 uniform cells but only ~1650 of these.
+//     xc   = max(x, clamp_lo)
+//     code = (entries[(bits(xc) >> 16) - first] + bits(xc)) >> 24
+//     entries[i] = (base << 24) + 2^24 - bits(threshold inside the cell, or the next cell's start)
+struct LogLut {
+  float clamp_lo = 0.f;           // bits(clamp_lo) has its low 16 bits clear and clamp_lo <= thr[1]
+  uint32_t first = 0;             // bits(clamp_lo) >> 16
+  std::vector<uint32_t> entries;  // (bits(1.0f) >> 16) - first + 1 words
+};
+// Fails (returns false) if some cell would hold two thresholds.
+bool build_log_lut(const StepFn &fn, LogLut *out);
+int log_lut_eval(const LogLut &lut, float x);
+
 // ---- matrix constants, computed in float32 exactly as BT709.h:389-397 ------------------
 struct MatrixConsts {
   float inv255;  // 1.0f/255.0f
