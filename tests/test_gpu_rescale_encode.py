@@ -38,6 +38,37 @@ def test_rescale_identity_size_is_identity():
     assert np.array_equal(out[0].cpu().numpy(), src)
 
 
+@pytest.mark.parametrize("iw,ih,ow,oh,frames", [(100, 70, 150, 101, 3), (96, 130, 97, 131, 2), (33, 65, 1030, 67, 2)])
+def test_rescale_batch_padded_pitches(iw, ih, ow, oh, frames):
+    """several frames, row pitches and frame strides wider than the image, guard bytes untouched;
+    near-unity scales make some source rows emit no output row (the walker must skip them)"""
+    from _gpu import ctx, dev
+    srcs = [bgra_random(iw, ih, seed=40 + f, alpha=None) for f in range(frames)]
+    big_in = torch.full((frames, ih + 3, iw + 5, 4), 0x5A, dtype=torch.uint8, device="cuda")
+    for f in range(frames):
+        big_in[f, :ih, :iw] = dev(srcs[f])
+    big_out = torch.full((frames, oh + 2, ow + 7, 4), 0xA5, dtype=torch.uint8, device="cuda")
+    ctx().rescale_bgra(big_in[:, :ih, :iw], big_out[:, :oh, :ow], wait=True)
+    got = big_out.cpu().numpy()
+    for f in range(frames):
+        _exact(got[f, :oh, :ow], ORA.rescale_bgra(srcs[f], ow, oh), f"frame {f}")
+    assert (got[:, oh:, :, :] == 0xA5).all() and (got[:, :, ow:, :] == 0xA5).all(), "wrote outside the image"
+
+
+def test_rescale_alpha_channel_is_linear():
+    """A is blended without the sRGB curve (the texture's alpha is linear): constant alpha stays constant,
+    and a vertical alpha ramp upscaled 2x matches the oracle"""
+    from _gpu import ctx, dev
+    src = bgra_random(64, 32, seed=9, alpha=None)
+    src[..., 3] = np.arange(32, dtype=np.uint8)[:, None] * 8
+    out = torch.zeros((1, 64, 128, 4), dtype=torch.uint8, device="cuda")
+    ctx().rescale_bgra(dev(src)[None], out, wait=True)
+    _exact(out[0].cpu().numpy(), ORA.rescale_bgra(src, 128, 64), "alpha ramp")
+    src[..., 3] = 200
+    ctx().rescale_bgra(dev(src)[None], out, wait=True)
+    assert (out[0, :, :, 3].cpu().numpy() == 200).all()
+
+
 def test_decode_rescale_policy():
     """O1 (AAPLRenderer.m:891-977): same size -> one pass; else decode -> intermediate -> rescale"""
     from _gpu import ctx, dev
