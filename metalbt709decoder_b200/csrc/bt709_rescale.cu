@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) k_rescale(const RescaleArgs p) {
 }
 
 // -------------------------------------------------------------------- rescale, column walker
-// Upscale / same-size fast path (scale <= 1 source pixel per output pixel in both directions).
+// Fast path for upscales, same size and moderate downscales (launch_rescale decides).
 // A warp owns a tile of 32 output columns x kWalkTH output rows; a thread owns one output column
 // and walks down the source rows the tile needs.  For each source row it converts its two
 // horizontal taps to linear light (256-entry tables replicated per lane: conflict-free) and blends
@@ -271,8 +271,10 @@ static size_t walk_smem_bytes(int enc_cells_log2, int rep_log2) {  // 64 KB of a
 }
 
 int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
-  // upscale or same size, and every output-row byte offset fits 32 bits: column walker
-  if (a.iw <= a.ow && a.ih <= a.oh && a.enc_cells_log2 <= 13 && (long long) a.oh * a.po < (1ll << 32) &&
+  // Column walker: any horizontal scale (two taps per column either way) and vertical scales up to 3 source
+  // rows per output row.  It blends every source row of the strip, so a vertical downscale by s costs ~s blends
+  // per output row; beyond 3 the per-pixel kernel (4 taps, no shared rows) is as good.  Offsets must fit 32 bits.
+  if ((long long) a.ih <= 3ll * a.oh && a.enc_cells_log2 <= 13 && (long long) a.oh * a.po < (1ll << 32) &&
       (long long) a.ih * a.pi < (1ll << 32) && a.pi >= 0 && a.po >= 0) {
     const long long tiles2 = (long long) a.nframes * ((a.ow + 31) / 32) * ((a.oh + kWalkTH - 1) / kWalkTH);
     const long long ctas = (tiles2 + kWalkWarps - 1) / kWalkWarps;

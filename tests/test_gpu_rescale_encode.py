@@ -18,7 +18,8 @@ def _exact(got, want, what):
 
 # ------------------------------------------------------------------------------ pass 2
 @pytest.mark.parametrize("iw,ih,ow,oh", [(1920, 1080, 2560, 1440), (64, 48, 64, 48), (64, 48, 31, 17), (5, 3, 40, 33),
-                                         (320, 240, 1, 1), (2, 2, 257, 3)])
+                                         (320, 240, 1, 1), (2, 2, 257, 3), (640, 360, 320, 180), (1000, 300, 77, 101),
+                                         (200, 301, 300, 100), (128, 400, 128, 99), (3840, 2160, 1280, 720)])
 def test_rescale_matches_oracle(iw, ih, ow, oh):
     """PARITY UNPINNED in the reference (no CPU twin); pinned to the restatement."""
     from _gpu import ctx, dev

@@ -1,0 +1,25 @@
+#!/usr/bin/env python3
+"""Time bt709_rescale_bgra for arbitrary sizes: python tools/time_rescale.py IW IH OW OH [frames]"""
+import sys
+import torch
+sys.path.insert(0, ".")
+import metalbt709decoder_b200 as pkg
+
+iw, ih, ow, oh = map(int, sys.argv[1:5])
+frames = int(sys.argv[5]) if len(sys.argv) > 5 else 64
+ctx = pkg.BT709Context(0)
+src = torch.randint(0, 256, (frames, ih, iw, 4), dtype=torch.uint8, device="cuda")
+dst = torch.zeros((frames, oh, ow, 4), dtype=torch.uint8, device="cuda")
+for _ in range(3):
+    ctx.rescale_bgra(src, dst)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+n = 10
+e0.record()
+for _ in range(n):
+    ctx.rescale_bgra(src, dst)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / n
+gb = frames * (iw * ih + ow * oh) * 4 / 1e9
+print(f"{iw}x{ih} -> {ow}x{oh} x{frames}: {ms:.3f} ms  {frames*iw*ih/ms/1e6:.1f} Gpix/s in  {frames*ow*oh/ms/1e6:.1f} Gpix/s out  {gb/ms*1e3:.0f} GB/s")
