@@ -573,7 +573,8 @@ static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t 
   const int active_warps = a0.tiles_per_row >= wpc ? wpc : a0.tiles_per_row * a0.rps;
   const size_t smem_ring = smem + (size_t) active_warps * kRingDepth * (ALPHA ? 640 : 384);
   static const bool no_ring = getenv("BT709_NO_RING") != nullptr;
-  const bool use_ring = smem_ring <= kMaxDynSmem && FULL && !no_ring && aligned(a0.y, 16) && aligned(a0.py, 16) && aligned(a0.sy, 16) &&
+  // (the ring kernel gives every warp one fixed tile column: rows wider than 32 tiles take the register path)
+  const bool use_ring = smem_ring <= kMaxDynSmem && a0.tiles_per_row <= wpc && FULL && !no_ring && aligned(a0.y, 16) && aligned(a0.py, 16) && aligned(a0.sy, 16) &&
                         aligned(a0.c, 16) && aligned(a0.pc, 16) && aligned(a0.sc, 16) &&
                         (!ALPHA || (aligned(a0.a, 16) && aligned(a0.pa, 16) && aligned(a0.sa, 16)));
   // frames per launch such that every 32-bit unit offset stays below 2^32

@@ -36,6 +36,16 @@ def test_random_frames_fast_path(gamma, w, h):
     _check(decode(gamma, y, c), ORA.decode_nv12(gamma, y, c), f"{w}x{h}")
 
 
+@pytest.mark.parametrize("w,h", [(7680, 8), (4224, 6), (8196, 4), (4096, 4), (5000, 3)])
+def test_rows_wider_than_32_tiles(w, h):
+    """more than 32 tiles of 128 pixels per row: the CTA's warps loop over the tile columns.  (The ring kernel
+    gives each warp ONE tile column and once decoded only the first 4096 pixels of such rows.)"""
+    from _gpu import decode
+    y, c = frame_random(w, h, seed=712)
+    for gamma in (0, 2):
+        _check(decode(gamma, y, c), ORA.decode_nv12(gamma, y, c), f"{w}x{h} gamma={gamma}")
+
+
 @pytest.mark.parametrize("gamma", GAMMAS)
 @pytest.mark.parametrize("w,h", [(37, 21), (1, 1), (2, 2), (3, 5), (130, 7), (258, 3)])
 def test_ragged_sizes_generic_path(gamma, w, h):
