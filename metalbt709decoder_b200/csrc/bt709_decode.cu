@@ -131,7 +131,7 @@ __device__ __forceinline__ void tile_load(const DecodeArgs &p, unsigned oy, unsi
 }
 
 template <int CL2, int RL2, bool ALPHA, bool FULL>
-__device__ __forceinline__ void tile_compute_store(const DecodeArgs &p, unsigned oo, unsigned rp, bool valid,
+__device__ __forceinline__ void tile_compute_store(const DecodeArgs &p, unsigned oo, unsigned rp, bool valid, bool half,
                                                    const TileLoad<ALPHA> &t, const DecodeK2 &k, float clamp_lo,
                                                    uint32_t sbase) {
   if (!FULL && !valid) return;
@@ -141,11 +141,17 @@ __device__ __forceinline__ void tile_compute_store(const DecodeArgs &p, unsigned
   f32x2 crn = mul2(add2(pku(magic_byte<1>(t.c), magic_byte<3>(t.c)), k.kC), k.inv255);
   f32x2 cb_g = mul2(cbn, k.g_cb), cb_b = mul2(cbn, k.b_cb);
   f32x2 cr_r = mul2(crn, k.r_cr), cr_g = mul2(crn, k.g_cr);
-  st_stream_u128((uint8_t *) ptr_mad(p.out, oo, 16),
-                 decode_row<CL2, RL2, ALPHA>(t.y0, t.a0, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
-  if (has_row1)
-    st_stream_u128((uint8_t *) ptr_mad(p.out, oo + p.po16, 16),
-                   decode_row<CL2, RL2, ALPHA>(t.y1, t.a1, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+  // half (w % 4 == 2 only): the last lane of a row owns two pixels and stores 8 bytes; its 4-byte loads stay
+  // inside the row pitch, which is a multiple of 4 on this path
+  auto store = [&](unsigned off16, uint4 v) {
+    uint8_t *dst = (uint8_t *) ptr_mad(p.out, off16, 16);
+    if (!FULL && half)
+      st_stream_u64(dst, make_uint2(v.x, v.y));
+    else
+      st_stream_u128(dst, v);
+  };
+  store(oo, decode_row<CL2, RL2, ALPHA>(t.y0, t.a0, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+  if (has_row1) store(oo + p.po16, decode_row<CL2, RL2, ALPHA>(t.y1, t.a1, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
 }
 
 // WRAP = false: the batch is one contiguous tall image (frame stride == rows * pitch for every
@@ -191,6 +197,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) 
   for (unsigned tile = tile0; tile < (unsigned) p.tiles_per_row; tile += p.tile_stride) {
     const unsigned col4 = tile * 32 + lane;  // column in 4-pixel units
     const bool valid = FULL || (int) (col4 * 4) < p.w;
+    const bool half = !FULL && (int) (col4 * 4 + 2) == p.w;  // w % 4 == 2: this lane owns the last two pixels
     // Two offset streams: the load stream runs PD steps ahead of the store stream.  Measured
     // (tools/probes/gran_bw.cu): with 1024 threads per SM the HBM pipe needs >= 24 B of loads in
     // flight per thread to reach 6 TB/s at this byte mix; 12 B (one step ahead) gave 4.4 TB/s.
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) 
           tile_load<ALPHA, FULL>(p, oy, oc, oa, rpl, valid, buf[(j + PD) % NB]);
           advance_load();
         }
-        tile_compute_store<CL2, RL2, ALPHA, FULL>(p, oo, rps_, valid, buf[j], k, clamp_lo, sbase);
+        tile_compute_store<CL2, RL2, ALPHA, FULL>(p, oo, rps_, valid, half, buf[j], k, clamp_lo, sbase);
         rps_ += p.d_rp;
         oo += p.dout;
         if (WRAP && rps_ >= rows2) { rps_ -= rows2; oo += p.wout; }
@@ -336,7 +343,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
       t.a1 = lds_u32(st + 512);
     }
     __syncwarp();  // every lane has its words before this slot is refilled
-    tile_compute_store<CL2, RL2, ALPHA, true>(p, oo, rps_, true, t, k, clamp_lo, sbase);
+    tile_compute_store<CL2, RL2, ALPHA, true>(p, oo, rps_, true, false, t, k, clamp_lo, sbase);
     rps_ += p.d_rp;
     oo += p.dout;
     if (WRAP && rps_ >= rows2) { rps_ -= rows2; oo += p.wout; }
@@ -493,7 +500,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_bulk(const DecodeArgs p) 
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(bar_empty + 8 * slot);
-    if (rpg < total_rp) tile_compute_store<CL2, RL2, ALPHA, true>(p, oo, rp, true, t, k, clamp_lo, sbase);
+    if (rpg < total_rp) tile_compute_store<CL2, RL2, ALPHA, true>(p, oo, rp, true, false, t, k, clamp_lo, sbase);
     // advance to this warp's row pair in the CTA's next band
     rpg += p.step_rp;
     rp += p.d_rp;
@@ -511,6 +518,8 @@ __global__ void __launch_bounds__(256) k_decode_generic(const DecodeArgs p) {
   const long long blocks = (long long) p.nframes * p.rows2 * cw;
   const float fN = (float) (1 << p.cells_log2);
   const float kY = 16.0f, kC = 128.0f;
+  // one 32-bit store per pixel whenever the output plane allows it (it almost always does)
+  const bool word_stores = (((unsigned long long) p.out | (unsigned long long) p.po | (unsigned long long) p.so) & 3ull) == 0;
   for (long long i = (long long) blockIdx.x * blockDim.x + threadIdx.x; i < blocks;
        i += (long long) gridDim.x * blockDim.x) {
     const int bx = (int) (i % cw);
@@ -543,7 +552,11 @@ __global__ void __launch_bounds__(256) k_decode_generic(const DecodeArgs p) {
           A = (uint32_t) round_pos(__fmul_rn(an, 255.0f));
         }
         uint8_t *o = p.out + f * p.so + (long long) row * p.po + (long long) col * 4;
-        o[0] = (uint8_t) B; o[1] = (uint8_t) G; o[2] = (uint8_t) R; o[3] = (uint8_t) A;
+        if (word_stores) {
+          *reinterpret_cast<uint32_t *>(o) = B | (G << 8) | (R << 16) | (A << 24);
+        } else {
+          o[0] = (uint8_t) B; o[1] = (uint8_t) G; o[2] = (uint8_t) R; o[3] = (uint8_t) A;
+        }
       }
     }
   }
@@ -729,7 +742,7 @@ int launch_decode(const DecodeArgs &a0, int sm_count, void *stream) {
   a.tile_stride = a.tiles_per_row >= wpc ? wpc : a.tiles_per_row;  // > 4096 px wide: warps loop over tiles
   const bool alpha = a.a != nullptr;
   const unsigned long long units = (unsigned long long) a.nframes * a.rows2 + 2ull * sm_count * 32;
-  bool fast = (a.w % 4 == 0) && aligned(a.y, 4) && aligned(a.py, 4) && aligned(a.sy, 4) && aligned(a.c, 4) &&
+  bool fast = (a.w % 2 == 0) && aligned(a.y, 4) && aligned(a.py, 4) && aligned(a.sy, 4) && aligned(a.c, 4) &&
               aligned(a.pc, 4) && aligned(a.sc, 4) && aligned(a.out, 16) && aligned(a.po, 16) &&
               aligned(a.so, 16) && units < 0x7FFFFFFFull && a.sy < (1ll << 32) && a.sc < (1ll << 32) &&
               a.so < (1ll << 34) && a.sa < (1ll << 32) && a.py < (1ll << 28) && a.pc < (1ll << 28) && a.po < (1ll << 30) &&

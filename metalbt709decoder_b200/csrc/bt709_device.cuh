@@ -38,6 +38,9 @@ __device__ __forceinline__ uint4 ld_stream_u128(const void *p) {
 __device__ __forceinline__ void st_stream_u128(void *p, uint4 v) {
   asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
+__device__ __forceinline__ void st_stream_u64(void *p, uint2 v) {
+  asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
 __device__ __forceinline__ void st_stream_u32(void *p, uint32_t v) {
   asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }

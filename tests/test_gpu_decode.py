@@ -90,6 +90,33 @@ def test_padded_pitches_and_unaligned_bases():
     _check(out[0, :, :w].cpu().numpy(), want, "unaligned")
 
 
+@pytest.mark.parametrize("w,h,alpha", [(854, 480, False), (1366, 768, False), (130, 6, True), (6, 2, False)])
+def test_even_widths_not_multiple_of_4_on_the_fast_path(w, h, alpha):
+    """w % 4 == 2 with 4-byte-aligned pitches (what CoreVideo hands over for 854x480 or 1366x768): the last
+    lane of a row owns two pixels only; the two pixels after the row end must stay untouched"""
+    from _gpu import ctx, dev
+    y, c = frame_random(w, h, seed=21, full_range=True)
+    F = 3
+    pw = (w + 3) // 4 * 4 + 4
+    ty = torch.full((F, h, pw), 0x11, dtype=torch.uint8, device="cuda")
+    tc = torch.full((F, h // 2, pw), 0x80, dtype=torch.uint8, device="cuda")
+    ty[:, :, :w] = dev(y)[None]
+    tc[:, :, :w] = dev(c)[None]
+    ta = None
+    if alpha:
+        ay, _ = frame_random(w, h, seed=22, full_range=True)
+        ta = torch.full((F, h, pw), 0x22, dtype=torch.uint8, device="cuda")
+        ta[:, :, :w] = dev(ay)[None]
+    out = torch.full((F, h, pw, 4), 0xEE, dtype=torch.uint8, device="cuda")
+    gamma = 1 if alpha else 3
+    ctx().decode_nv12(gamma, ty[:, :, :w], tc[:, :, :w], out[:, :, :w], alpha_y=None if ta is None else ta[:, :, :w], wait=True)
+    want = ORA.decode_nv12(gamma, y, c, alpha_y=ay if alpha else None)
+    got = out.cpu().numpy()
+    for f in range(F):
+        _check(got[f, :, :w], want, f"{w}x{h} frame {f}")
+    assert (got[:, :, w:] == 0xEE).all(), "wrote past the end of a row"
+
+
 def test_batch_of_frames_matches_per_frame():
     from _gpu import ctx, dev
     w, h, F = 640, 360, 5

@@ -14,7 +14,7 @@ ctx = pkg.BT709Context(0)
 cw = (w + 1) // 2 * 2
 y = torch.randint(16, 236, (frames, h, w + pad), dtype=torch.uint8, device="cuda")[:, :, :w]
 c = torch.randint(16, 241, (frames, (h + 1) // 2, cw + pad), dtype=torch.uint8, device="cuda")[:, :, :cw]
-out = torch.zeros((frames, h, w + pad // 4, 4), dtype=torch.uint8, device="cuda")[:, :, :w]
+out = torch.zeros((frames, h, w + pad, 4), dtype=torch.uint8, device="cuda")[:, :, :w]
 def run():
     if encode:
         ctx.encode_bgra_to_nv12(1, 0, out, y, c)
