@@ -123,7 +123,8 @@ __device__ __forceinline__ f32x2 add2_rz(f32x2 a, f32x2 b) {
 // exact a + b where a (or b) may be the result of a packed multiply: never contracted
 __device__ __forceinline__ f32x2 add2_nc(f32x2 a, f32x2 b, const EncK &k) { return fma2_rn(a, k.one, b); }
 
-template <bool WRAP>
+// FULL = (w % 128 == 0): no per-lane predicates; otherwise the lanes past the row end load nothing and store nothing
+template <bool WRAP, bool FULL>
 __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
   // [0, 64 KB): float2 table, entry b replica r at byte b*256 + r*8;  then the chroma cell LUT
@@ -164,6 +165,7 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   const unsigned f0 = rpg0 / rows2, rp0 = rpg0 - f0 * rows2;
   const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;
   const unsigned col4 = tile * 32 + lane;
+  const bool valid = FULL || (int) (col4 * 4) < p.w;
   unsigned oi = f0 * p.si16 + rp0 * 2 * p.pi16 + col4;  // BGRA in, 16-byte units
   unsigned oy = f0 * p.sy4 + rp0 * 2 * p.py4 + col4;    // Y out, 4-byte units
   unsigned oc = f0 * p.sc4 + rp0 * p.pc4 + col4;        // CbCr out, 4-byte units
@@ -188,14 +190,17 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   // one-step register prefetch: the loads of step k+1 are issued before the math of step k
   // (without it 40 % of the warp samples sat on the first use of the loaded pixels)
   unsigned rpl = rp0;
-  uint4 na = ld_stream_u128(ptr_mad(p.in, oi, 16));
-  uint4 nb = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
+  uint4 na = make_uint4(0, 0, 0, 0), nb = na;
+  if (valid) {
+    na = ld_stream_u128(ptr_mad(p.in, oi, 16));
+    nb = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
+  }
   for (unsigned kk = 0; kk < nsteps; kk++) {
     const uint4 a = na, b = nb;
     rpl += p.d_rp;
     oi += p.di;
     if (WRAP && rpl >= rows2) { rpl -= rows2; oi += p.wi; }
-    if (kk + 1 < nsteps) {
+    if (kk + 1 < nsteps && valid) {
       na = ld_stream_u128(ptr_mad(p.in, oi, 16));
       nb = ld_stream_u128(ptr_mad(p.in, oi + p.pi16, 16));
     }
@@ -244,9 +249,11 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
     uint32_t cbA, cbB, crA, crB;
     upku(mb, cbA, cbB); upku(mr, crA, crB);
     const uint32_t cw = __byte_perm(__byte_perm(cbA, crA, 0x0051), __byte_perm(cbB, crB, 0x0051), 0x5410);
-    st_stream_u32((void *) ptr_mad(p.y, oy, 4), yw[0]);
-    st_stream_u32((void *) ptr_mad(p.y, oy + p.py4, 4), yw[1]);
-    st_stream_u32((void *) ptr_mad(p.c, oc, 4), cw);
+    if (valid) {
+      st_stream_u32((void *) ptr_mad(p.y, oy, 4), yw[0]);
+      st_stream_u32((void *) ptr_mad(p.y, oy + p.py4, 4), yw[1]);
+      st_stream_u32((void *) ptr_mad(p.c, oc, 4), cw);
+    }
     rp += p.d_rp;
     oy += p.dy; oc += p.dc;
     if (WRAP && rp >= rows2) { rp -= rows2; oy += p.wy; oc += p.wc; }
@@ -257,8 +264,9 @@ static int launch_encode_fast(const EncodeArgs &a0, int sm_count, cudaStream_t s
   EncodeArgs a = a0;
   const int rows2 = a.h / 2;
   const int wpc = 32;
-  a.tiles_per_row = a.w / 128;
+  a.tiles_per_row = (a.w + 127) / 128;
   a.rps = wpc / a.tiles_per_row;
+  const bool full = a.w % 128 == 0;
   const bool contiguous = a.nframes == 1 || (a.si == (long long) a.h * a.pi && a.sy == (long long) a.h * a.py &&
                                              a.sc == (long long) rows2 * a.pc);
   bool wrap = true;
@@ -275,10 +283,13 @@ static int launch_encode_fast(const EncodeArgs &a0, int sm_count, cudaStream_t s
   a.wi = a.si16 - r2 * 2 * a.pi16; a.wy = a.sy4 - r2 * 2 * a.py4; a.wc = a.sc4 - r2 * a.pc4;
   a.one = 1.0f;
   const size_t smem = 65536 + ((size_t) (1 << a.out_cells_log2) + 1) * 32;
-  if (wrap)
-    k_encode_fast<true><<<grid, 1024, smem, s>>>(a);
-  else
-    k_encode_fast<false><<<grid, 1024, smem, s>>>(a);
+  if (wrap) {
+    if (full) k_encode_fast<true, true><<<grid, 1024, smem, s>>>(a);
+    else k_encode_fast<true, false><<<grid, 1024, smem, s>>>(a);
+  } else {
+    if (full) k_encode_fast<false, true><<<grid, 1024, smem, s>>>(a);
+    else k_encode_fast<false, false><<<grid, 1024, smem, s>>>(a);
+  }
   return (int) cudaGetLastError();
 }
 
@@ -287,9 +298,9 @@ int launch_encode(const EncodeArgs &a, int sm_count, void *stream) {
   const size_t smem = (512 + (size_t) (1 << a.out_cells_log2) + 1) * 4;
   const bool vec = (a.w % 4 == 0) && aligned(a.in, 16) && aligned(a.pi, 16) && aligned(a.si, 16) && aligned(a.y, 4) &&
                    aligned(a.py, 4) && aligned(a.sy, 4) && aligned(a.c, 4) && aligned(a.pc, 4) && aligned(a.sc, 4);
-  // fast path: whole 128-pixel tiles, at most 32 tiles per row, offsets that fit 32-bit units
+  // fast path: widths that are a multiple of 4, at most 32 tiles of 128 pixels per row, offsets that fit 32-bit units
   const unsigned long long in_bytes = (unsigned long long) a.nframes * (a.si > 0 ? a.si : (long long) a.h * a.pi);
-  if (vec && a.w % 128 == 0 && a.w <= 4096 && in_bytes < 0xFFFF0000ull * 16 && a.si >= 0 && a.sy >= 0 && a.sc >= 0 &&
+  if (vec && a.w <= 4096 && in_bytes < 0xFFFF0000ull * 16 && a.si >= 0 && a.sy >= 0 && a.sc >= 0 &&
       a.out_cells_log2 <= 12)
     return launch_encode_fast(a, sm_count, s);
   const long long n = (long long) a.nframes * (a.h / 2) * (vec ? a.w / 4 : a.w / 2);
@@ -304,8 +315,11 @@ int launch_encode(const EncodeArgs &a, int sm_count, void *stream) {
 
 int encode_kernels_init() {
   int e;
-  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4097 * 32))) return e;
-  return (int) cudaFuncSetAttribute(k_encode_fast<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536 + 4097 * 32);
+  const int smem = 65536 + 4097 * 32;
+  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+  if ((e = (int) cudaFuncSetAttribute(k_encode_fast<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem))) return e;
+  return (int) cudaFuncSetAttribute(k_encode_fast<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 }  // namespace bt709

@@ -107,7 +107,7 @@ def _encode(gin, gout, bgra, pad=0):
 
 
 @pytest.mark.parametrize("gin,gout", PAIRS)
-@pytest.mark.parametrize("w,h", [(2048, 64), (6, 4), (130, 2)])
+@pytest.mark.parametrize("w,h", [(2048, 64), (6, 4), (130, 2), (720, 6), (1440, 4), (132, 6), (4092, 2), (4, 2)])
 def test_encode420_matches_oracle(gin, gout, w, h):
     bgra = bgra_random(w, h, seed=711)
     gy, gc = _encode(gin, gout, bgra, pad=(2 if w % 4 else 0))
