@@ -190,7 +190,9 @@ __global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const Resca
     const int x0 = min(max(xi, 0), p.iw - 1), x1 = min(max(xi + 1, 0), p.iw - 1);
     const f32x2 fx2 = pk(fx, fx);
     const uint8_t *src0 = p.in + (long long) f * p.si + (size_t) x0 * 4;
-    uint8_t *dp = p.out + (long long) f * p.so + (size_t) min(ox, p.ow - 1) * 4 + (size_t) oy0 * po;
+    // output row pointer: stepped BEFORE each row is computed (stepping after the store made the compiler keep
+    // a copy of the old pointer alive), so it starts one row above the tile
+    uint8_t *dp = p.out + (long long) f * p.so + (size_t) min(ox, p.ow - 1) * 4 + (long long) (oy0 - 1) * (long long) po;
 
     auto blend = [&](uint32_t w0, uint32_t w1) -> Lin4 {  // top/bot of the oracle: t0 + fx * (t1 - t0)
       const Lin4 t0 = texel(w0), t1 = texel(w1);
@@ -231,7 +233,6 @@ __global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const Resca
       const uint32_t bg = __byte_perm(sb, sg, 0x0073);
       const uint32_t w = __byte_perm(bg, __byte_perm(sr, __float_as_uint(ta), 0x0053), 0x5410);
       if (live) *reinterpret_cast<uint32_t *>(dp) = w;
-      dp += po;
     };
 
     // ---- walk.  H[j & 1] = blended row y, H[(j + 1) & 1] = blended row y + 1; the raw taps of the
@@ -255,6 +256,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const Resca
         H[(j + 1) & 1] = blend(q0[j % kWalkPD], q1[j % kWalkPD]);                 // row min(y + 1, ih - 1)
         fetch(y + 1 + kWalkPD, q0[j % kWalkPD], q1[j % kWalkPD]);                 // refill the slot
         while ((int) info.y <= y) {  // emit the output rows whose top tap is y (<=: can never spin)
+          dp += po;
           emit(__uint_as_float(info.x), H[j & 1], H[(j + 1) & 1]);
           ip += 16;
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(info.x), "=r"(info.y), "=r"(info.z), "=r"(info.w) : "r"(ip));
