@@ -278,14 +278,25 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
   // per output row; beyond 3 the per-pixel kernel (4 taps, no shared rows) is as good.  Offsets must fit 32 bits.
   if ((long long) a.ih <= 3ll * a.oh && a.enc_cells_log2 <= 13 && (long long) a.oh * a.po < (1ll << 32) &&
       (long long) a.ih * a.pi < (1ll << 32) && a.pi >= 0 && a.po >= 0) {
-    const long long tiles2 = (long long) a.nframes * ((a.ow + 31) / 32) * ((a.oh + kWalkTH - 1) / kWalkTH);
-    const long long ctas = (tiles2 + kWalkWarps - 1) / kWalkWarps;
-    long long grid2 = ctas < (long long) sm_count ? ctas : (long long) sm_count;
-    if (walk_smem_bytes(a.enc_cells_log2, 2) <= kMaxDynSmem)
-      k_rescale_cols<2><<<(unsigned) grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(a);
-    else
-      k_rescale_cols<0><<<(unsigned) grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 0), (cudaStream_t) stream>>>(a);
-    return (int) cudaGetLastError();
+    // the kernel counts warp tiles in 32 bits: split batches with more than 2^31 of them across launches
+    const long long tiles_per_frame = (long long) ((a.ow + 31) / 32) * ((a.oh + kWalkTH - 1) / kWalkTH);
+    long long frames_per_launch = (1ll << 31) / tiles_per_frame;
+    if (frames_per_launch < 1) frames_per_launch = 1;
+    for (long long f0 = 0; f0 < a.nframes; f0 += frames_per_launch) {
+      RescaleArgs b = a;
+      b.nframes = (int) (a.nframes - f0 < frames_per_launch ? a.nframes - f0 : frames_per_launch);
+      b.in = a.in + f0 * a.si;
+      b.out = a.out + f0 * a.so;
+      const long long ctas = (b.nframes * tiles_per_frame + kWalkWarps - 1) / kWalkWarps;
+      const unsigned grid2 = (unsigned) (ctas < (long long) sm_count ? ctas : (long long) sm_count);
+      if (walk_smem_bytes(a.enc_cells_log2, 2) <= kMaxDynSmem)
+        k_rescale_cols<2><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(b);
+      else
+        k_rescale_cols<0><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 0), (cudaStream_t) stream>>>(b);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return (int) e;
+    }
+    return 0;
   }
   const size_t smem = (256 + (size_t) (1 << a.enc_cells_log2) + 1) * 4;
   const long long tiles = (long long) a.nframes * ((a.ow + 31) / 32) * ((a.oh + 7) / 8);
