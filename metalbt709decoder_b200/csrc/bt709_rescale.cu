@@ -94,21 +94,27 @@ struct Lin4 {
   f32x2 rg, ba;  // (R, G), (B, A) in linear light (A is linear already)
 };
 
-template <int ERL2>  // log2 of the encode-LUT replication (bank-conflict relief: lanes use replica lane % R)
-__global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const RescaleArgs p) {
-  extern __shared__ __align__(16) uint32_t s_mem[];
-  // Layout (dynamic shared memory, kWalkSmem bytes):
-  //   [lin table, 64 KB, placed at the first 64 KB-ALIGNED shared address]
-  //     word b*64 + r      : sRGB byte b -> linear float, replica r (one per lane)
-  //     word b*64 + 32 + r : alpha byte b -> b * (1/255), replica r
-  //     entry stride 256 B and 64 KB alignment: the lookup address is ONE PRMT of the texel word and a
-  //     per-lane register holding (table address | lane << 2), no add
-  //   [row info, kWalkWarps slices]  in the alignment gap in front of the table when it fits, else after it
-  //   [encode cell LUT, R interleaved replicas: cell i of replica r at word i*R + r]  after the table
+struct WalkTables {
+  uint32_t lin_lane;   // shared address of the {linear, alpha} byte table | lane << 2 (the PRMT operand)
+  uint32_t rows_base;  // shared address of this warp's row-info slice
+  uint32_t enc_base;   // encode-LUT base with the 2^23 index bias and the lane's replica folded in
+};
+
+// Fills the CTA's tables (all threads, ends with a __syncthreads) and returns the per-thread addresses.
+// Layout (dynamic shared memory):
+//   [lin table, 64 KB, placed at the first 64 KB-ALIGNED shared address]
+//     word b*64 + r      : sRGB byte b -> linear float, replica r (one per lane)
+//     word b*64 + 32 + r : alpha byte b -> b * (1/255), replica r
+//     entry stride 256 B and 64 KB alignment: the lookup address is ONE PRMT of the texel word and a
+//     per-lane register holding (table address | lane << 2), no add
+//   [row info, one slice per warp]  in the alignment gap in front of the table when it fits, else after it
+//   [encode cell LUT, R interleaved replicas: cell i of replica r at word i*R + r]  after the table
+template <int ERL2, int WARPS>
+__device__ __forceinline__ WalkTables walk_tables(const RescaleArgs &p, uint32_t *s_mem) {
   const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_mem);
   const uint32_t pad = (0x10000u - (smem0 & 0xFFFFu)) & 0xFFFFu;
   float *s_lin = reinterpret_cast<float *>(s_mem + (pad >> 2));
-  constexpr int kRowWords = kWalkWarps * kWalkRowInfo;
+  constexpr int kRowWords = WARPS * kWalkRowInfo;
   const bool rows_in_gap = pad >= kRowWords * 4;
   uint32_t *s_after = s_mem + (pad >> 2) + 256 * 64;
   uint32_t *s_rows = rows_in_gap ? s_mem : s_after;
@@ -124,9 +130,19 @@ __global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const Resca
   if (threadIdx.x == 0) s_enc[-1] = (uint32_t) __cvta_generic_to_shared(s_enc) - (0x4B000000u << (2 + ERL2));
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lin_lane = (smem0 + pad) | (lane << 2);  // bytes 3,2: table address; byte 0: lane * 4
-  const uint32_t rows_base = (uint32_t) __cvta_generic_to_shared(s_rows + warp * kWalkRowInfo);
-  const uint32_t enc_base = *reinterpret_cast<volatile uint32_t *>(s_enc - 1) + ((lane & ((1 << ERL2) - 1)) << 2);
+  WalkTables t;
+  t.lin_lane = (smem0 + pad) | (lane << 2);
+  t.rows_base = (uint32_t) __cvta_generic_to_shared(s_rows + warp * kWalkRowInfo);
+  t.enc_base = *reinterpret_cast<volatile uint32_t *>(s_enc - 1) + ((lane & ((1 << ERL2) - 1)) << 2);
+  return t;
+}
+
+template <int ERL2>  // log2 of the encode-LUT replication (bank-conflict relief: lanes use replica lane % R)
+__global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const RescaleArgs p) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  const WalkTables wt = walk_tables<ERL2, kWalkWarps>(p, s_mem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lin_lane = wt.lin_lane, rows_base = wt.rows_base, enc_base = wt.enc_base;
   const float fN = (float) (1 << p.enc_cells_log2);
   const float clamp_lo = p.enc_clamp_lo;
   const f32x2 one = pk(p.one, p.one), neg1 = pk(-1.0f, -1.0f);
@@ -268,6 +284,159 @@ __global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const Resca
   }
 }
 
+// -------------------------------------------------------------- rescale, two columns per thread
+// Same walk, but a thread owns TWO adjacent output columns (a warp: 64 columns x kWalkTH rows).  For horizontal scales <= 1 the taps of the two columns lie in
+// three consecutive (clamped) source texels p0 <= p1 <= p2: column a uses (T0, T1), column b uses (T0, T1) or
+// (T1, T2).  Per source row that is 3 loads and 3 texel conversions instead of 4 + 4, one pointer update, one
+// loop; per output row one row-info read, one pointer step and one 8-byte store for both pixels.
+// 24 warps x 80 registers measured best (16 warps: latency-bound, 32 warps x 64 registers: same as 24).
+constexpr int kWalk2Warps = 24;
+
+template <int ERL2>
+__global__ void __launch_bounds__(kWalk2Warps * 32, 1) k_rescale_cols2(const RescaleArgs p) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  const WalkTables wt = walk_tables<ERL2, kWalk2Warps>(p, s_mem);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lin_lane = wt.lin_lane, rows_base = wt.rows_base, enc_base = wt.enc_base;
+  const float fN = (float) (1 << p.enc_cells_log2);
+  const float clamp_lo = p.enc_clamp_lo;
+  const f32x2 one = pk(p.one, p.one), neg1 = pk(-1.0f, -1.0f);
+  const f32x2 fN2 = pk(fN, fN), magic2 = pk(8388608.0f, 8388608.0f);
+
+  auto lin_of = [&](uint32_t px, uint32_t sel, int extra) -> float {
+    const uint32_t addr = __byte_perm(px, lin_lane, sel);
+    float v;
+    if (extra)
+      asm("ld.shared.f32 %0, [%1+128];" : "=f"(v) : "r"(addr));
+    else
+      asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+  };
+  auto texel = [&](uint32_t px) -> Lin4 {
+    Lin4 t;
+    t.rg = pk(lin_of(px, 0x7624, 0), lin_of(px, 0x7614, 0));
+    t.ba = pk(lin_of(px, 0x7604, 0), lin_of(px, 0x7634, 1));
+    return t;
+  };
+  auto enc_idx = [&](float t) -> uint32_t {
+    uint32_t e;
+    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((__float_as_uint(t) << (2 + ERL2)) + enc_base));
+    return e;
+  };
+  auto lerp = [&](const Lin4 &t0, const Lin4 &t1, f32x2 f2) -> Lin4 {  // t0 + f * (t1 - t0), the oracle's steps
+    Lin4 h;
+    h.rg = fma2_rn(mul2(f2, fma2_rn(t0.rg, neg1, t1.rg)), one, t0.rg);
+    h.ba = fma2_rn(mul2(f2, fma2_rn(t0.ba, neg1, t1.ba)), one, t0.ba);
+    return h;
+  };
+  auto pixel = [&](const Lin4 &v) -> uint32_t {  // linear (R,G),(B,A) -> BGRA8 word (sRGB encode, alpha linear)
+    float vr, vg, vb, va, tr_, tg_, tb_;
+    upk(v.rg, vr, vg);
+    upk(v.ba, vb, va);
+    vr = fmaxf(vr, clamp_lo); vg = fmaxf(vg, clamp_lo); vb = fmaxf(vb, clamp_lo);
+    upk(fma2_rz(pk(vr, vg), fN2, magic2), tr_, tg_);
+    asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(tb_) : "f"(vb), "f"(fN));
+    const uint32_t sr = enc_idx(tr_) + __float_as_uint(vr);
+    const uint32_t sg = enc_idx(tg_) + __float_as_uint(vg);
+    const uint32_t sb = enc_idx(tb_) + __float_as_uint(vb);
+    float ta;
+    asm("add.rz.f32 %0, %1, 0f47000080;" : "=f"(ta) : "f"(__fmul_rn(va, 255.0f)));
+    const uint32_t bg = __byte_perm(sb, sg, 0x0073);
+    return __byte_perm(bg, __byte_perm(sr, __float_as_uint(ta), 0x0053), 0x5410);
+  };
+
+  const int tiles_x = (p.ow + 63) >> 6, tiles_y = (p.oh + kWalkTH - 1) / kWalkTH;
+  const unsigned tiles_per_frame = tiles_x * tiles_y;
+  const unsigned tiles = (unsigned) p.nframes * tiles_per_frame;
+  const int ylast = p.ih - 1, xlast = p.iw - 1;
+  const unsigned pi = (unsigned) p.pi, po = (unsigned) p.po;
+  for (unsigned t = blockIdx.x * kWalk2Warps + warp; t < tiles; t += gridDim.x * kWalk2Warps) {
+    const unsigned f = t / tiles_per_frame, tr = t - f * tiles_per_frame;
+    const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+    const int oy0 = ty * kWalkTH;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < kWalkTH / 32; k++) {
+      const int r = k * 32 + lane, oy = oy0 + r;
+      const float sy = __fadd_rn(__fmul_rn(__fadd_rn((float) oy, 0.5f), p.scale_y), -0.5f);
+      const float fy0 = floorf(sy);
+      asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(rows_base + r * 16), "r"(__float_as_uint(__fsub_rn(sy, fy0))),
+                   "r"(oy < p.oh ? (uint32_t) (int) fy0 : 0x7fffffffu) : "memory");
+    }
+    if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1,%1};" ::"r"(rows_base + kWalkTH * 16), "r"(0x7fffffffu) : "memory");
+    __syncwarp();
+
+    // ---- the two columns of this thread
+    const int oxa = tx * 64 + lane * 2;
+    const bool live_a = oxa < p.ow, live_b = oxa + 1 < p.ow;
+    const float sxa = __fadd_rn(__fmul_rn(__fadd_rn((float) oxa, 0.5f), p.scale_x), -0.5f);
+    const float sxb = __fadd_rn(__fmul_rn(__fadd_rn((float) (oxa + 1), 0.5f), p.scale_x), -0.5f);
+    const float fxa0 = floorf(sxa), fxb0 = floorf(sxb);
+    const int xia = (int) fxa0, xib = (int) fxb0;      // xib - xia is 0 or 1 for scales <= 1
+    const bool bsel = xib != xia;                      // column b uses (T1, T2) instead of (T0, T1)
+    const f32x2 fxa2 = pk(__fsub_rn(sxa, fxa0), __fsub_rn(sxa, fxa0));
+    const f32x2 fxb2 = pk(__fsub_rn(sxb, fxb0), __fsub_rn(sxb, fxb0));
+    const int p0 = min(max(xia, 0), xlast), p1 = min(max(xia + 1, 0), xlast), p2 = min(max(xia + 2, 0), xlast);
+    const unsigned d1 = (unsigned) (p1 - p0) * 4u, d2 = (unsigned) (p2 - p0) * 4u;  // 0/4 and 0/4/8 (clamped edges)
+    const uint8_t *src0 = p.in + (long long) f * p.si + (size_t) p0 * 4;
+    uint8_t *dp = p.out + (long long) f * p.so + (size_t) min(oxa, p.ow - 1) * 4 + (long long) (oy0 - 1) * (long long) po;
+    const bool wide_store = live_b && ((reinterpret_cast<uintptr_t>(dp) | po) & 7u) == 0;
+
+    const uint8_t *fp = nullptr;
+    auto fetch = [&](int row, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
+      w0 = __ldg(reinterpret_cast<const uint32_t *>(fp));
+      w1 = __ldg(reinterpret_cast<const uint32_t *>(fp + d1));
+      w2 = __ldg(reinterpret_cast<const uint32_t *>(fp + d2));
+      fp += (unsigned) row < (unsigned) ylast ? pi : 0u;
+    };
+    auto blend2 = [&](uint32_t w0, uint32_t w1, uint32_t w2, Lin4 &ha, Lin4 &hb) {
+      const Lin4 t0 = texel(w0), t1 = texel(w1), t2 = texel(w2);
+      ha = lerp(t0, t1, fxa2);
+      Lin4 u0, u1;
+      u0.rg = bsel ? t1.rg : t0.rg; u0.ba = bsel ? t1.ba : t0.ba;
+      u1.rg = bsel ? t2.rg : t1.rg; u1.ba = bsel ? t2.ba : t1.ba;
+      hb = lerp(u0, u1, fxb2);
+    };
+
+    uint32_t ip = rows_base;
+    uint32_t info_fy, info_y;
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(info_fy), "=r"(info_y) : "r"(ip));
+    int y = (int) info_y;
+    uint32_t q0[kWalkPD], q1[kWalkPD], q2[kWalkPD], a0w, a1w, a2w;
+    fp = ptr_mad(src0, (unsigned) max(y, 0), pi);
+    fetch(y, a0w, a1w, a2w);
+#pragma unroll
+    for (int j = 0; j < kWalkPD; j++) fetch(y + 1 + j, q0[j], q1[j], q2[j]);
+    Lin4 Ha[2], Hb[2];
+    blend2(a0w, a1w, a2w, Ha[0], Hb[0]);
+    bool done = false;
+    while (!done) {
+#pragma unroll
+      for (int j = 0; j < 2 * kWalkPD; j++) {
+        blend2(q0[j % kWalkPD], q1[j % kWalkPD], q2[j % kWalkPD], Ha[(j + 1) & 1], Hb[(j + 1) & 1]);
+        fetch(y + 1 + kWalkPD, q0[j % kWalkPD], q1[j % kWalkPD], q2[j % kWalkPD]);
+        while ((int) info_y <= y) {
+          dp += po;
+          const float fy = __uint_as_float(info_fy);
+          const f32x2 fy2 = pk(fy, fy);
+          const uint32_t wa = pixel(lerp(Ha[j & 1], Ha[(j + 1) & 1], fy2));
+          const uint32_t wb = pixel(lerp(Hb[j & 1], Hb[(j + 1) & 1], fy2));
+          if (wide_store) {
+            *reinterpret_cast<uint2 *>(dp) = make_uint2(wa, wb);
+          } else {
+            if (live_a) *reinterpret_cast<uint32_t *>(dp) = wa;
+            if (live_b) *reinterpret_cast<uint32_t *>(dp + 4) = wb;
+          }
+          ip += 16;
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(info_fy), "=r"(info_y) : "r"(ip));
+        }
+        y++;
+        if (info_y == 0x7fffffffu) { done = true; break; }
+      }
+    }
+  }
+}
+
 static size_t walk_smem_bytes(int enc_cells_log2, int rep_log2) {  // 64 KB of alignment slack in front of the table
   return 65536 + (256 * 64 + (size_t) kWalkWarps * kWalkRowInfo + 4 + ((((size_t) 1 << enc_cells_log2) + 1) << rep_log2)) * 4;
 }
@@ -289,7 +458,14 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
       b.out = a.out + f0 * a.so;
       const long long ctas = (b.nframes * tiles_per_frame + kWalkWarps - 1) / kWalkWarps;
       const unsigned grid2 = (unsigned) (ctas < (long long) sm_count ? ctas : (long long) sm_count);
-      if (walk_smem_bytes(a.enc_cells_log2, 2) <= kMaxDynSmem)
+      static const bool no_cols2 = getenv("BT709_NO_COLS2") != nullptr;
+      if (a.iw <= a.ow && !no_cols2 && walk_smem_bytes(a.enc_cells_log2, 2) <= kMaxDynSmem) {
+        // horizontal scale <= 1: two adjacent columns per thread share their middle texel
+        const long long tiles64 = (long long) ((a.ow + 63) / 64) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
+        const long long ctas2 = (tiles64 + kWalk2Warps - 1) / kWalk2Warps;
+        const unsigned g2 = (unsigned) (ctas2 < (long long) sm_count ? ctas2 : (long long) sm_count);
+        k_rescale_cols2<2><<<g2, kWalk2Warps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(b);
+      } else if (walk_smem_bytes(a.enc_cells_log2, 2) <= kMaxDynSmem)
         k_rescale_cols<2><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(b);
       else
         k_rescale_cols<0><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 0), (cudaStream_t) stream>>>(b);
@@ -307,6 +483,8 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
 
 int rescale_kernels_init() {
   int e = (int) cudaFuncSetAttribute(k_rescale_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_rescale_cols2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
   if (e) return e;
   return (int) cudaFuncSetAttribute(k_rescale_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) walk_smem_bytes(13, 0));
 }
