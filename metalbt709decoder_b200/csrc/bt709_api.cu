@@ -270,6 +270,9 @@ int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, in
   a.scale_y = (float) in_h / (float) out_h;
   a.lin256 = ctx->lin256[kSrgb];
   a.enc_lut = ctx->fl_lut[kSrgb]; a.enc_clamp_lo = ctx->fl_clamp[kSrgb]; a.enc_cells_log2 = ctx->fl_cells[kSrgb];
+  // the decoder's Linear-mode step function IS the sRGB encode (decode_code(kLinear) == from_linear_code(kSrgb))
+  a.enc_log_lut = ctx->dec_log_lut; a.enc_log_clamp_lo = ctx->dec_log_clamp;
+  a.enc_log_cells = ctx->dec_log_cells; a.enc_log_first = ctx->dec_log_first;
   a.one = 1.0f;
   return finish(ctx, launch_rescale(a, ctx->sm_count, stream), stream, wait);
 }

@@ -47,6 +47,11 @@ struct RescaleArgs {
   const uint32_t *enc_lut;  // linear float -> sRGB byte (cell LUT)
   float enc_clamp_lo;
   int enc_cells_log2;
+  // optional log-cell form of the same encode step function (bt709_tables.h: LogLut); nullptr = none
+  const uint32_t *enc_log_lut;
+  float enc_log_clamp_lo;
+  int enc_log_cells;
+  unsigned enc_log_first;
   float one;  // 1.0f, deliberately a runtime value (blocks FFMA2 contraction, see k_rescale_cols)
 };
 

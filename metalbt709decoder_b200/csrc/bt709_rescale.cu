@@ -109,25 +109,33 @@ struct WalkTables {
 //     per-lane register holding (table address | lane << 2), no add
 //   [row info, one slice per warp]  in the alignment gap in front of the table when it fits, else after it
 //   [encode cell LUT, R interleaved replicas: cell i of replica r at word i*R + r]  after the table
-template <int ERL2, int WARPS>
+// ELOG: the encode LUT is the log-cell form (index = upper half of the float) with 2^ERL2 replicas.  It is too big
+// for the space behind the aligned table, so it goes FIRST and the table follows at the next 64 KB boundary:
+//   [encode log-cell LUT][pad][lin table @ 64 KB boundary][row info]
+template <int ERL2, int WARPS, bool ELOG = false>
 __device__ __forceinline__ WalkTables walk_tables(const RescaleArgs &p, uint32_t *s_mem) {
   const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_mem);
-  const uint32_t pad = (0x10000u - (smem0 & 0xFFFFu)) & 0xFFFFu;
-  float *s_lin = reinterpret_cast<float *>(s_mem + (pad >> 2));
   constexpr int kRowWords = WARPS * kWalkRowInfo;
-  const bool rows_in_gap = pad >= kRowWords * 4;
+  const int nenc = (ELOG ? p.enc_log_cells : (1 << p.enc_cells_log2) + 1) << ERL2;
+  const uint32_t head = ELOG ? (uint32_t) (nenc + 4) * 4u : 0u;  // bytes in front of the table's alignment pad
+  const uint32_t pad = head + ((0x10000u - ((smem0 + head) & 0xFFFFu)) & 0xFFFFu);
+  float *s_lin = reinterpret_cast<float *>(s_mem + (pad >> 2));
+  const bool rows_in_gap = !ELOG && pad >= kRowWords * 4;
   uint32_t *s_after = s_mem + (pad >> 2) + 256 * 64;
   uint32_t *s_rows = rows_in_gap ? s_mem : s_after;
-  uint32_t *s_enc = s_after + (rows_in_gap ? 0 : kRowWords) + 4;
-  const int nenc = ((1 << p.enc_cells_log2) + 1) << ERL2;
+  uint32_t *s_enc = ELOG ? s_mem + 4 : s_after + (rows_in_gap ? 0 : kRowWords) + 4;
+  if (ELOG && pad + 65536u + kRowWords * 4u > (uint32_t) kMaxDynSmem) __trap();  // dynamic shared memory starts 1 KB into the window
   for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
     s_lin[(i >> 5) * 64 + (i & 31)] = __ldg(&p.lin256[i >> 5]);
     s_lin[(i >> 5) * 64 + 32 + (i & 31)] = __fmul_rn((float) (i >> 5), 1.0f / 255.0f);
   }
-  for (int i = threadIdx.x; i < nenc; i += blockDim.x) s_enc[i] = __ldg(&p.enc_lut[i >> ERL2]);
-  // the encode-LUT address is (bits(2^23 + idx) << 2) + enc_base with the 2^23 folded into enc_base; it
-  // goes through shared memory so that ptxas sees an opaque register and emits a single LEA per lookup
-  if (threadIdx.x == 0) s_enc[-1] = (uint32_t) __cvta_generic_to_shared(s_enc) - (0x4B000000u << (2 + ERL2));
+  const uint32_t *glut = ELOG ? p.enc_log_lut : p.enc_lut;
+  for (int i = threadIdx.x; i < nenc; i += blockDim.x) s_enc[i] = __ldg(&glut[i >> ERL2]);
+  // the encode-LUT address is (index register << 2) + enc_base, the index register holding 2^23 + cell (uniform
+  // cells) or first + cell (log cells): the bias is folded into enc_base, which goes through shared memory so
+  // that ptxas sees an opaque register and emits a single LEA per lookup
+  if (threadIdx.x == 0)
+    s_enc[-1] = (uint32_t) __cvta_generic_to_shared(s_enc) - ((ELOG ? p.enc_log_first : 0x4B000000u) << (2 + ERL2));
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   WalkTables t;
@@ -292,14 +300,14 @@ __global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const Resca
 // 24 warps x 80 registers measured best (16 warps: latency-bound, 32 warps x 64 registers: same as 24).
 constexpr int kWalk2Warps = 24;
 
-template <int ERL2>
+template <int ERL2, bool ELOG>
 __global__ void __launch_bounds__(kWalk2Warps * 32, 1) k_rescale_cols2(const RescaleArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
-  const WalkTables wt = walk_tables<ERL2, kWalk2Warps>(p, s_mem);
+  const WalkTables wt = walk_tables<ERL2, kWalk2Warps, ELOG>(p, s_mem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lin_lane = wt.lin_lane, rows_base = wt.rows_base, enc_base = wt.enc_base;
   const float fN = (float) (1 << p.enc_cells_log2);
-  const float clamp_lo = p.enc_clamp_lo;
+  const float clamp_lo = ELOG ? p.enc_log_clamp_lo : p.enc_clamp_lo;
   const f32x2 one = pk(p.one, p.one), neg1 = pk(-1.0f, -1.0f);
   const f32x2 fN2 = pk(fN, fN), magic2 = pk(8388608.0f, 8388608.0f);
 
@@ -334,8 +342,14 @@ __global__ void __launch_bounds__(kWalk2Warps * 32, 1) k_rescale_cols2(const Res
     upk(v.rg, vr, vg);
     upk(v.ba, vb, va);
     vr = fmaxf(vr, clamp_lo); vg = fmaxf(vg, clamp_lo); vb = fmaxf(vb, clamp_lo);
-    upk(fma2_rz(pk(vr, vg), fN2, magic2), tr_, tg_);
-    asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(tb_) : "f"(vb), "f"(fN));
+    if (ELOG) {  // log cells: the index is the upper half of the float (PRMT, see lut2 in bt709_decode.cu)
+      tr_ = __uint_as_float(__byte_perm(__float_as_uint(vr), 0, 0x4432));
+      tg_ = __uint_as_float(__byte_perm(__float_as_uint(vg), 0, 0x4432));
+      tb_ = __uint_as_float(__byte_perm(__float_as_uint(vb), 0, 0x4432));
+    } else {
+      upk(fma2_rz(pk(vr, vg), fN2, magic2), tr_, tg_);
+      asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(tb_) : "f"(vb), "f"(fN));
+    }
     const uint32_t sr = enc_idx(tr_) + __float_as_uint(vr);
     const uint32_t sg = enc_idx(tg_) + __float_as_uint(vg);
     const uint32_t sb = enc_idx(tb_) + __float_as_uint(vb);
@@ -464,7 +478,11 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
         const long long tiles64 = (long long) ((a.ow + 63) / 64) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
         const long long ctas2 = (tiles64 + kWalk2Warps - 1) / kWalk2Warps;
         const unsigned g2 = (unsigned) (ctas2 < (long long) sm_count ? ctas2 : (long long) sm_count);
-        k_rescale_cols2<2><<<g2, kWalk2Warps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(b);
+        static const bool no_elog = getenv("BT709_NO_ELOG") != nullptr;
+        if (b.enc_log_lut && !no_elog && (size_t) b.enc_log_cells * 64 + 16 <= 0x1FC00 - 0x400)
+          k_rescale_cols2<4, true><<<g2, kWalk2Warps * 32, kMaxDynSmem, (cudaStream_t) stream>>>(b);
+        else
+          k_rescale_cols2<2, false><<<g2, kWalk2Warps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(b);
       } else if (walk_smem_bytes(a.enc_cells_log2, 2) <= kMaxDynSmem)
         k_rescale_cols<2><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(b);
       else
@@ -484,7 +502,9 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
 int rescale_kernels_init() {
   int e = (int) cudaFuncSetAttribute(k_rescale_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
   if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_rescale_cols2<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  e = (int) cudaFuncSetAttribute(k_rescale_cols2<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_rescale_cols2<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
   if (e) return e;
   return (int) cudaFuncSetAttribute(k_rescale_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) walk_smem_bytes(13, 0));
 }
