@@ -145,14 +145,15 @@ __device__ __forceinline__ WalkTables walk_tables(const RescaleArgs &p, uint32_t
   return t;
 }
 
-template <int ERL2>  // log2 of the encode-LUT replication (bank-conflict relief: lanes use replica lane % R)
+// ERL2: log2 of the encode-LUT replication (bank-conflict relief: lanes use replica lane % R); ELOG: log-cell LUT
+template <int ERL2, bool ELOG>
 __global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const RescaleArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
-  const WalkTables wt = walk_tables<ERL2, kWalkWarps>(p, s_mem);
+  const WalkTables wt = walk_tables<ERL2, kWalkWarps, ELOG>(p, s_mem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lin_lane = wt.lin_lane, rows_base = wt.rows_base, enc_base = wt.enc_base;
   const float fN = (float) (1 << p.enc_cells_log2);
-  const float clamp_lo = p.enc_clamp_lo;
+  const float clamp_lo = ELOG ? p.enc_log_clamp_lo : p.enc_clamp_lo;
   const f32x2 one = pk(p.one, p.one), neg1 = pk(-1.0f, -1.0f);
   const f32x2 fN2 = pk(fN, fN), magic2 = pk(8388608.0f, 8388608.0f);
 
@@ -246,8 +247,14 @@ __global__ void __launch_bounds__(kWalkWarps * 32, 1) k_rescale_cols(const Resca
       upk(vrg, vr, vg);
       upk(vba, vb, va);
       vr = fmaxf(vr, clamp_lo); vg = fmaxf(vg, clamp_lo); vb = fmaxf(vb, clamp_lo);
-      upk(fma2_rz(pk(vr, vg), fN2, magic2), tr_, tg_);
-      asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(tb_) : "f"(vb), "f"(fN));
+      if (ELOG) {  // log cells: the index is the upper half of the float
+        tr_ = __uint_as_float(__byte_perm(__float_as_uint(vr), 0, 0x4432));
+        tg_ = __uint_as_float(__byte_perm(__float_as_uint(vg), 0, 0x4432));
+        tb_ = __uint_as_float(__byte_perm(__float_as_uint(vb), 0, 0x4432));
+      } else {
+        upk(fma2_rz(pk(vr, vg), fN2, magic2), tr_, tg_);
+        asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(tb_) : "f"(vb), "f"(fN));
+      }
       const uint32_t sr = enc_idx(tr_) + __float_as_uint(vr);  // byte 3 = sRGB code
       const uint32_t sg = enc_idx(tg_) + __float_as_uint(vg);
       const uint32_t sb = enc_idx(tb_) + __float_as_uint(vb);
@@ -473,20 +480,25 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
       const long long ctas = (b.nframes * tiles_per_frame + kWalkWarps - 1) / kWalkWarps;
       const unsigned grid2 = (unsigned) (ctas < (long long) sm_count ? ctas : (long long) sm_count);
       static const bool no_cols2 = getenv("BT709_NO_COLS2") != nullptr;
-      if (a.iw <= a.ow && !no_cols2 && walk_smem_bytes(a.enc_cells_log2, 2) <= kMaxDynSmem) {
+      static const bool no_elog = getenv("BT709_NO_ELOG") != nullptr;
+      const size_t smem_u = walk_smem_bytes(a.enc_cells_log2, 2);  // uniform-cell LUT, 4 replicas
+      // log-cell LUT with 16 replicas: it must end before the 64 KB boundary the table is placed on
+      const bool elog = b.enc_log_lut && !no_elog && (size_t) b.enc_log_cells * 64 + 16 <= 0x1F800;
+      cudaStream_t st = (cudaStream_t) stream;
+      if (a.iw <= a.ow && !no_cols2 && (elog || smem_u <= kMaxDynSmem)) {
         // horizontal scale <= 1: two adjacent columns per thread share their middle texel
         const long long tiles64 = (long long) ((a.ow + 63) / 64) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
         const long long ctas2 = (tiles64 + kWalk2Warps - 1) / kWalk2Warps;
         const unsigned g2 = (unsigned) (ctas2 < (long long) sm_count ? ctas2 : (long long) sm_count);
-        static const bool no_elog = getenv("BT709_NO_ELOG") != nullptr;
-        if (b.enc_log_lut && !no_elog && (size_t) b.enc_log_cells * 64 + 16 <= 0x1FC00 - 0x400)
-          k_rescale_cols2<4, true><<<g2, kWalk2Warps * 32, kMaxDynSmem, (cudaStream_t) stream>>>(b);
-        else
-          k_rescale_cols2<2, false><<<g2, kWalk2Warps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(b);
-      } else if (walk_smem_bytes(a.enc_cells_log2, 2) <= kMaxDynSmem)
-        k_rescale_cols<2><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 2), (cudaStream_t) stream>>>(b);
-      else
-        k_rescale_cols<0><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 0), (cudaStream_t) stream>>>(b);
+        if (elog) k_rescale_cols2<4, true><<<g2, kWalk2Warps * 32, kMaxDynSmem, st>>>(b);
+        else k_rescale_cols2<2, false><<<g2, kWalk2Warps * 32, smem_u, st>>>(b);
+      } else if (elog) {
+        k_rescale_cols<4, true><<<grid2, kWalkWarps * 32, kMaxDynSmem, st>>>(b);
+      } else if (smem_u <= kMaxDynSmem) {
+        k_rescale_cols<2, false><<<grid2, kWalkWarps * 32, smem_u, st>>>(b);
+      } else {
+        k_rescale_cols<0, false><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 0), st>>>(b);
+      }
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return (int) e;
     }
@@ -500,13 +512,13 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
 }
 
 int rescale_kernels_init() {
-  int e = (int) cudaFuncSetAttribute(k_rescale_cols<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
-  if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_rescale_cols2<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
-  if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_rescale_cols2<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
-  if (e) return e;
-  return (int) cudaFuncSetAttribute(k_rescale_cols<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) walk_smem_bytes(13, 0));
+  const int m = (int) kMaxDynSmem;
+  int e;
+  if ((e = (int) cudaFuncSetAttribute(k_rescale_cols<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m))) return e;
+  if ((e = (int) cudaFuncSetAttribute(k_rescale_cols<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m))) return e;
+  if ((e = (int) cudaFuncSetAttribute(k_rescale_cols<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m))) return e;
+  if ((e = (int) cudaFuncSetAttribute(k_rescale_cols2<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m))) return e;
+  return (int) cudaFuncSetAttribute(k_rescale_cols2<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m);
 }
 
 }  // namespace bt709
