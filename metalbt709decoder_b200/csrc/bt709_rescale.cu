@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(256) k_rescale(const RescaleArgs p) {
 }
 
 // -------------------------------------------------------------------- rescale, column walker
-// Fast path for upscales, same size and moderate downscales (launch_rescale decides).
+// Fast path for upscales, same size and moderate downscales (launch_rescale decides; when the horizontal
+// scale is <= 1 it prefers k_rescale_cols2 below, which shares this design with two columns per thread).
 // A warp owns a tile of 32 output columns x kWalkTH output rows; a thread owns one output column
 // and walks down the source rows the tile needs.  For each source row it converts its two
 // horizontal taps to linear light (256-entry tables replicated per lane: conflict-free) and blends
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(256) k_rescale(const RescaleArgs p) {
 //
 // Everything that depends on the output row only (fy, the top source row, the row index)
 // is warp-uniform: the warp computes it once per tile, one row per lane, into its own slice of
-// shared memory, and the row loop reads it back with one LDS.128 per output row.  The walker runs
+// shared memory, and the row loop reads it back with one LDS.64 per output row.  The walker runs
 // over UNCLAMPED source rows (top row -1 at the upper edge) and clamps only the row it fetches, so
 // the clamped-edge cases of the oracle (both taps on the same row) need no special code.
 //
@@ -97,7 +98,7 @@ struct Lin4 {
 struct WalkTables {
   uint32_t lin_lane;   // shared address of the {linear, alpha} byte table | lane << 2 (the PRMT operand)
   uint32_t rows_base;  // shared address of this warp's row-info slice
-  uint32_t enc_base;   // encode-LUT base with the 2^23 index bias and the lane's replica folded in
+  uint32_t enc_base;   // encode-LUT base with the index bias and the lane's replica folded in
 };
 
 // Fills the CTA's tables (all threads, ends with a __syncthreads) and returns the per-thread addresses.
