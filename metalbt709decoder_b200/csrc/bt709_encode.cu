@@ -111,6 +111,11 @@ __global__ void __launch_bounds__(256) k_encode(const EncodeArgs p) {
 //     the IEEE quotient for every value this path can produce (all 2^24 8-bit RGB triples checked
 //     on the host: tests/test_tables_cpu.py) and costs 3 instructions instead of ~10;
 //   * round() of the positive results is one add.rz(+32768.5): the code is byte 1 of the float.
+#ifndef BT709_ENC_FENCE
+#define BT709_ENC_FENCE 2
+#endif
+constexpr int kEncFence = BT709_ENC_FENCE;  // pixels per dependence group
+
 struct EncK {
   f32x2 one, kr, kg, kb, s224, o128, rcb, ncb, rcr, ncr, quarter, rnd, inv255, nmagic;
 };
@@ -209,23 +214,30 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
     // an LDS.64 dictates where its results land: 23 % of the loop was register moves).  The
     // linear-light sums accumulate in the reference's order ((NW + NE) + SW) + SE (BT709.h:1182-1183).
     uint32_t yw[2];
-    float sum[2][3] = {};  // [block A/B][R,G,B]
-#pragma unroll 1
-    for (int r = 0; r < 2; r++) {  // a real loop: unrolled, the 24 hoisted LDS.64 results spill the loop state
+    float sum[2][3];  // [block A/B][R,G,B]
+    uint32_t fence = 0;  // always 0; carries a data dependence from one pixel group to the next
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
       float ty[4];
       const uint4 row = r ? b : a;
 #pragma unroll
       for (int i = 0; i < 4; i++) {
-        const uint32_t px = i == 0 ? row.x : i == 1 ? row.y : i == 2 ? row.z : row.w;
+        // Unrolled, ptxas hoists all 24 LDS.64 of the step (48 result registers) and spills the loop state; a
+        // rolled row loop costs ~35 instructions of control per step.  Instead every FENCE-th pixel word is
+        // OR-ed with (bits of the previous luma & zero), zero being a run-time 0: one LOP3 that changes
+        // nothing but makes the pixel's table addresses depend on the previous group's result.
+        uint32_t px = i == 0 ? row.x : i == 1 ? row.y : i == 2 ? row.z : row.w;
+        if ((r * 4 + i) % kEncFence == 0 && (r | i)) px |= fence;
         float l[3], c[3];
         fetch(px, 16, l[0], c[0]); fetch(px, 8, l[1], c[1]); fetch(px, 0, l[2], c[2]);
         // Ey of BT709.h:223, then round(Ey*219 + 16) (BT709.h:234, 245): the integer part of
         // RZ(x + 32768.5) sits in byte 1 of the float
         const float ey = __fadd_rn(__fadd_rn(__fmul_rn(0.2126f, c[0]), __fmul_rn(0.7152f, c[1])), __fmul_rn(0.0722f, c[2]));
         asm("add.rz.f32 %0, %1, 0f47000080;" : "=f"(ty[i]) : "f"(__fadd_rn(__fmul_rn(ey, 219.0f), 16.0f)));
+        if ((r * 4 + i + 1) % kEncFence == 0) fence = __float_as_uint(ty[i]) & p.zero;
 #pragma unroll
         for (int ch = 0; ch < 3; ch++)
-          sum[i >> 1][ch] = (i & 1) == 0 ? (r == 0 ? l[ch] : __fadd_rn(sum[i >> 1][ch], l[ch])) : __fadd_rn(sum[i >> 1][ch], l[ch]);
+          sum[i >> 1][ch] = (r == 0 && (i & 1) == 0) ? l[ch] : __fadd_rn(sum[i >> 1][ch], l[ch]);
       }
       yw[r] = __byte_perm(__byte_perm(__float_as_uint(ty[0]), __float_as_uint(ty[1]), 0x0051),
                           __byte_perm(__float_as_uint(ty[2]), __float_as_uint(ty[3]), 0x0051), 0x5410);
@@ -282,6 +294,7 @@ static int launch_encode_fast(const EncodeArgs &a0, int sm_count, cudaStream_t s
   a.di = d_f * a.si16 + a.d_rp * 2 * a.pi16; a.dy = d_f * a.sy4 + a.d_rp * 2 * a.py4; a.dc = d_f * a.sc4 + a.d_rp * a.pc4;
   a.wi = a.si16 - r2 * 2 * a.pi16; a.wy = a.sy4 - r2 * 2 * a.py4; a.wc = a.sc4 - r2 * a.pc4;
   a.one = 1.0f;
+  a.zero = 0;
   const size_t smem = 65536 + ((size_t) (1 << a.out_cells_log2) + 1) * 32;
   if (wrap) {
     if (full) k_encode_fast<true, true><<<grid, 1024, smem, s>>>(a);

@@ -69,6 +69,7 @@ struct EncodeArgs {
   int tiles_per_row, rps;
   unsigned step_rp, d_rp, pi16, py4, pc4, si16, sy4, sc4, di, dy, dc, wi, wy, wc;
   float one;  // 1.0f, deliberately a runtime value
+  unsigned zero;  // 0, deliberately a runtime value (scheduling fence by data dependence, see k_encode_fast)
 };
 
 struct Packed444Args {
