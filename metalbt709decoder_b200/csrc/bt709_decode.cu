@@ -281,15 +281,32 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
   k.magic = pk(8388608.0f, 8388608.0f);
   k.one = pk(p.one, p.one);
 
-  const unsigned r_local = warp / p.tiles_per_row;
-  if (r_local >= (unsigned) p.rps) return;
-  const unsigned tile = warp - r_local * p.tiles_per_row;
-  const unsigned rows2 = p.rows2;
-  const unsigned total_rp = (unsigned) p.nframes * rows2;
-  const unsigned rpg0 = blockIdx.x * p.rps + r_local;
-  if (rpg0 >= total_rp) return;
-  const unsigned f0 = rpg0 / rows2, rp0 = rpg0 - f0 * rows2;
-  const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;
+  // this warp's first tile: band layout (fixed tile column, the row pair steps) or linear tile order (the
+  // tile column steps and wraps into the next row pair; WRAP only, one tall image: see DecodeArgs.linear_tiles)
+  unsigned tile, rows2, f0, rp0, nsteps, rpl;
+  if (WRAP && p.linear_tiles) {
+    const unsigned T = p.linear_tiles, total = (unsigned) p.rows2 * T, S = gridDim.x * (THREADS / 32);
+    const unsigned t0 = blockIdx.x * (THREADS / 32) + warp;
+    if (t0 >= total) return;
+    rp0 = t0 / T;
+    tile = t0 - rp0 * T;
+    f0 = 0;
+    rows2 = T;    // the wrap test below compares the stepped tile column with the tiles per row
+    rpl = tile;
+    nsteps = (total - t0 + S - 1) / S;
+  } else {
+    const unsigned r_local = warp / p.tiles_per_row;
+    if (r_local >= (unsigned) p.rps) return;
+    tile = warp - r_local * p.tiles_per_row;
+    rows2 = p.rows2;
+    const unsigned total_rp = (unsigned) p.nframes * rows2;
+    const unsigned rpg0 = blockIdx.x * p.rps + r_local;
+    if (rpg0 >= total_rp) return;
+    f0 = rpg0 / rows2;
+    rp0 = rpg0 - f0 * rows2;
+    rpl = rp0;
+    nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;
+  }
 
   // ---- copy role of this lane: which plane row it fetches, as base + 32-bit offset in 4-byte units
   const int role = lane >> 3, sub = lane & 7;  // 0: Y row 0, 1: Y row 1, 2: CbCr, 3: idle (alpha: second pass)
@@ -301,7 +318,6 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
   // alpha rows (ALPHA only): lanes 0-7 row 0, lanes 8-15 row 1, via a second cp.async
   unsigned aoff = ALPHA ? f0 * p.sa4 + (rp0 * 2 + (role & 1)) * p.pa4 + tile * 32 + sub * 4 : 0;
   const uint32_t adst = 384 + (role & 1) * 128 + sub * 16;
-  unsigned rpl = rp0;
 
   auto issue = [&](uint32_t slot) {
     if (role < 3)
@@ -321,7 +337,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
 
   const unsigned col4 = tile * 32 + lane;
   unsigned oo = f0 * p.so16 + rp0 * 2 * p.po16 + col4;
-  unsigned rps_ = rp0;
+  unsigned rps_ = rpl;  // store-side copy of the wrap counter (row pair, or tile column in linear order)
 #pragma unroll
   for (int j = 0; j < D - 1; j++) {
     if ((unsigned) j < nsteps) issue(j);
@@ -583,7 +599,8 @@ static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t 
   // ring slices exist for the warps that have a tile only.  The fully replicated log-cell LUT (209 KB)
   // leaves room for 30 of them (1920 or 3840 wide, no alpha); otherwise that mode prefetches in registers
   const int wpc = kDecodeThreads / 32;
-  const int active_warps = a0.tiles_per_row >= wpc ? wpc : a0.tiles_per_row * a0.rps;
+  const bool linear = WRAP && a0.linear_tiles != 0;  // linear tile order: every warp has a tile
+  const int active_warps = (linear || a0.tiles_per_row >= wpc) ? wpc : a0.tiles_per_row * a0.rps;
   const size_t smem_ring = smem + (size_t) active_warps * kRingDepth * (ALPHA ? 640 : 384);
   static const bool no_ring = getenv("BT709_NO_RING") != nullptr;
   // (the ring kernel gives every warp one fixed tile column: rows wider than 32 tiles take the register path)
@@ -648,6 +665,19 @@ static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t 
     a.wc = a.sc4 - a.rows2 * a.pc4;
     a.wa = a.sa4 - a.rows2 * 2 * a.pa4;
     a.wout = a.so16 - a.rows2 * 2 * a.po16;
+    if (linear && use_ring) {
+      // one tall image, tiles taken in row-major order, 32 per CTA and step: the "wrap" is the end of a row
+      const unsigned T = (unsigned) a.tiles_per_row, total_tiles = (unsigned) a.rows2 * T;
+      grid = (total_tiles + wpc - 1) / wpc;
+      if (grid > (unsigned) sm_count) grid = sm_count;
+      const unsigned S = grid * wpc, drp = S / T, dcol = S - drp * T;
+      a.d_rp = dcol;
+      a.dy = drp * 2 * a.py4 + dcol * 32; a.dc = drp * a.pc4 + dcol * 32;
+      a.da = drp * 2 * a.pa4 + dcol * 32; a.dout = drp * 2 * a.po16 + dcol * 32;
+      a.wy = 2 * a.py4 - T * 32; a.wc = a.pc4 - T * 32; a.wa = 2 * a.pa4 - T * 32; a.wout = 2 * a.po16 - T * 32;
+    } else {
+      a.linear_tiles = 0;
+    }
     if (use_ring)
       kring<<<grid, kDecodeThreads, smem_ring, s>>>(a);
     else
@@ -726,6 +756,14 @@ static int launch_decode_fast(const DecodeArgs &a0, int sm_count, cudaStream_t s
     a.h *= a.nframes;
     a.rows2 *= a.nframes;
     a.nframes = 1;
+    // rows of 15 or 30 tiles (1920, 3840 wide) leave 2 of the 32 warps idle in the band layout: take the tiles
+    // in linear order instead (ring kernel only; falls back to the band layout when the ring is not usable)
+    static const bool no_linear = getenv("BT709_NO_LINEAR") != nullptr;
+    const int wpc = kDecodeThreads / 32;
+    if (!no_linear && a.tiles_per_row < wpc && wpc % a.tiles_per_row != 0) {
+      a.linear_tiles = a.tiles_per_row;
+      return launch_decode_fast2<CL2, RL2, ALPHA, true, true>(a, sm_count, s);
+    }
     return launch_decode_fast2<CL2, RL2, ALPHA, true, false>(a, sm_count, s);
   }
   return launch_decode_fast2<CL2, RL2, ALPHA, true, true>(a, sm_count, s);

@@ -23,6 +23,11 @@ struct DecodeArgs {
   unsigned sy4, sc4, sa4, so16;         // frame strides in units
   unsigned dy, dc, da, dout;            // offset increment per step
   unsigned wy, wc, wa, wout;            // extra increment when the row pair wraps into the next frame
+  // ring kernel, linear tile order (launcher sets it for contiguous batches whose rows have fewer than 32 tiles
+  // and leave warps idle in the band layout): 0 = band layout, else tiles per row.  The 32 warps of a CTA then
+  // take 32 consecutive tiles of the row-major tile sequence; the per-step increments step the tile COLUMN and
+  // the wrap increments fire when the column passes the end of the row (same code as the frame wrap).
+  int linear_tiles;
   // bulk-staged kernel: shared-memory ring geometry
   int nstages, stage_bytes, nrows;      // ring depth; bytes per stage; rows (= bulk copies) per stage
   const uint32_t *lut;  // cell LUT of the selected gamma, N + 1 words, device memory

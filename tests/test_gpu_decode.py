@@ -117,6 +117,28 @@ def test_even_widths_not_multiple_of_4_on_the_fast_path(w, h, alpha):
     assert (got[:, :, w:] == 0xEE).all(), "wrote past the end of a row"
 
 
+@pytest.mark.parametrize("w,h,F,alpha", [(384, 6, 7, False), (1920, 4, 3, False), (3840, 2, 2, False), (640, 10, 4, True),
+                                         (1152, 6, 5, False)])
+def test_linear_tile_order_on_contiguous_batches(w, h, F, alpha):
+    """rows of 3, 5, 9, 15 or 30 tiles do not divide the CTA's 32 warps: contiguous batches are then decoded in
+    linear tile order (the tile column steps and wraps into the next row pair, across frame seams too)"""
+    from _gpu import ctx, dev
+    frames = [frame_random(w, h, seed=300 + f) for f in range(F)]
+    ty = torch.stack([dev(y) for y, _ in frames])
+    tc = torch.stack([dev(c) for _, c in frames])
+    ta = None
+    if alpha:
+        alphas = [frame_random(w, h, seed=400 + f, full_range=True)[0] for f in range(F)]
+        ta = torch.stack([dev(a) for a in alphas])
+    out = torch.zeros((F, h, w, 4), dtype=torch.uint8, device="cuda")
+    gamma = 1 if alpha else 0
+    ctx().decode_nv12(gamma, ty, tc, out, alpha_y=ta, wait=True)
+    got = out.cpu().numpy()
+    for f in range(F):
+        want = ORA.decode_nv12(gamma, frames[f][0], frames[f][1], alpha_y=alphas[f] if alpha else None)
+        _check(got[f], want, f"{w}x{h} frame {f}")
+
+
 def test_batch_of_frames_matches_per_frame():
     from _gpu import ctx, dev
     w, h, F = 640, 360, 5
