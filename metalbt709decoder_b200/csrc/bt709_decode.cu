@@ -760,7 +760,10 @@ static int launch_decode_fast(const DecodeArgs &a0, int sm_count, cudaStream_t s
     // in linear order instead (ring kernel only; falls back to the band layout when the ring is not usable)
     static const bool no_linear = getenv("BT709_NO_LINEAR") != nullptr;
     const int wpc = kDecodeThreads / 32;
-    if (!no_linear && a.tiles_per_row < wpc && wpc % a.tiles_per_row != 0) {
+    // (only if the ring still fits with all 32 warps active: the 209 KB log-cell LUT leaves room for 30)
+    const size_t lut_bytes = (size_t) (CL2 ? (1 << CL2) + 1 : a.log_cells) * (1 << RL2) * 4;
+    const bool ring_fits = lut_bytes + (size_t) wpc * kRingDepth * (ALPHA ? 640 : 384) <= kMaxDynSmem;
+    if (!no_linear && ring_fits && a.tiles_per_row < wpc && wpc % a.tiles_per_row != 0) {
       a.linear_tiles = a.tiles_per_row;
       return launch_decode_fast2<CL2, RL2, ALPHA, true, true>(a, sm_count, s);
     }
