@@ -171,6 +171,9 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;
   const unsigned col4 = tile * 32 + lane;
   const bool valid = FULL || (int) (col4 * 4) < p.w;
+  // w % 4 == 2: the last lane of a row owns one 2x2 block only and stores 2 bytes per plane row; its 16-byte
+  // loads stay inside the row pitch (a multiple of 16 on this path)
+  const bool half = !FULL && (int) (col4 * 4 + 2) == p.w;
   unsigned oi = f0 * p.si16 + rp0 * 2 * p.pi16 + col4;  // BGRA in, 16-byte units
   unsigned oy = f0 * p.sy4 + rp0 * 2 * p.py4 + col4;    // Y out, 4-byte units
   unsigned oc = f0 * p.sc4 + rp0 * p.pc4 + col4;        // CbCr out, 4-byte units
@@ -261,7 +264,11 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
     uint32_t cbA, cbB, crA, crB;
     upku(mb, cbA, cbB); upku(mr, crA, crB);
     const uint32_t cw = __byte_perm(__byte_perm(cbA, crA, 0x0051), __byte_perm(cbB, crB, 0x0051), 0x5410);
-    if (valid) {
+    if (!FULL && half) {
+      *reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(ptr_mad(p.y, oy, 4))) = (uint16_t) yw[0];
+      *reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(ptr_mad(p.y, oy + p.py4, 4))) = (uint16_t) yw[1];
+      *reinterpret_cast<uint16_t *>(const_cast<uint8_t *>(ptr_mad(p.c, oc, 4))) = (uint16_t) cw;
+    } else if (valid) {
       st_stream_u32((void *) ptr_mad(p.y, oy, 4), yw[0]);
       st_stream_u32((void *) ptr_mad(p.y, oy + p.py4, 4), yw[1]);
       st_stream_u32((void *) ptr_mad(p.c, oc, 4), cw);
@@ -309,11 +316,13 @@ static int launch_encode_fast(const EncodeArgs &a0, int sm_count, cudaStream_t s
 int launch_encode(const EncodeArgs &a, int sm_count, void *stream) {
   cudaStream_t s = (cudaStream_t) stream;
   const size_t smem = (512 + (size_t) (1 << a.out_cells_log2) + 1) * 4;
+  const bool al = aligned(a.in, 16) && aligned(a.pi, 16) && aligned(a.si, 16) && aligned(a.y, 4) && aligned(a.py, 4) &&
+                  aligned(a.sy, 4) && aligned(a.c, 4) && aligned(a.pc, 4) && aligned(a.sc, 4);
   const bool vec = (a.w % 4 == 0) && aligned(a.in, 16) && aligned(a.pi, 16) && aligned(a.si, 16) && aligned(a.y, 4) &&
                    aligned(a.py, 4) && aligned(a.sy, 4) && aligned(a.c, 4) && aligned(a.pc, 4) && aligned(a.sc, 4);
-  // fast path: widths that are a multiple of 4, at most 32 tiles of 128 pixels per row, offsets that fit 32-bit units
+  // fast path: aligned planes (any even width), at most 32 tiles of 128 pixels per row, offsets that fit 32-bit units
   const unsigned long long in_bytes = (unsigned long long) a.nframes * (a.si > 0 ? a.si : (long long) a.h * a.pi);
-  if (vec && a.w <= 4096 && in_bytes < 0xFFFF0000ull * 16 && a.si >= 0 && a.sy >= 0 && a.sc >= 0 &&
+  if (al && a.w <= 4096 && in_bytes < 0xFFFF0000ull * 16 && a.si >= 0 && a.sy >= 0 && a.sc >= 0 &&
       a.out_cells_log2 <= 12)
     return launch_encode_fast(a, sm_count, s);
   const long long n = (long long) a.nframes * (a.h / 2) * (vec ? a.w / 4 : a.w / 2);

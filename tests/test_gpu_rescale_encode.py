@@ -116,6 +116,28 @@ def test_encode420_matches_oracle(gin, gout, w, h):
     _exact(gc, wc, "CbCr")
 
 
+@pytest.mark.parametrize("w,h", [(854, 480), (1366, 8), (130, 4), (6, 2)])
+def test_encode_even_widths_not_multiple_of_4_on_the_fast_path(w, h):
+    """w % 4 == 2 with 16-byte-aligned BGRA pitch and 4-byte-aligned Y / CbCr pitches: the last lane of a row
+    owns one 2x2 block and stores 2 bytes per plane row; bytes past the row end stay untouched"""
+    from _gpu import ctx, dev
+    F = 2
+    imgs = [bgra_random(w, h, seed=800 + f) for f in range(F)]
+    pw = w + 2
+    tin = torch.full((F, h, pw, 4), 0x33, dtype=torch.uint8, device="cuda")
+    for f in range(F):
+        tin[f, :, :w] = dev(imgs[f])
+    ty = torch.full((F, h, pw), 0xEE, dtype=torch.uint8, device="cuda")
+    tc = torch.full((F, h // 2, pw), 0xDD, dtype=torch.uint8, device="cuda")
+    ctx().encode_bgra_to_nv12(GAMMA_SRGB, GAMMA_APPLE, tin[:, :, :w], ty[:, :, :w], tc[:, :, :w], wait=True)
+    gy, gc = ty.cpu().numpy(), tc.cpu().numpy()
+    for f in range(F):
+        wy, wc = ORA.encode_bgra_nv12(GAMMA_SRGB, GAMMA_APPLE, imgs[f])
+        _exact(gy[f, :, :w], wy, f"Y frame {f}")
+        _exact(gc[f, :, :w], wc, f"CbCr frame {f}")
+    assert (gy[:, :, w:] == 0xEE).all() and (gc[:, :, w:] == 0xDD).all(), "wrote past the end of a row"
+
+
 def test_encode_ramp_and_alpha_ignored():
     """F-ramp (gamma_write.m:280-298); the A byte is ignored (CVPixelBufferUtils.h:304-318)"""
     bgra = frame_ramp(1024, 8)
