@@ -71,7 +71,7 @@ struct EncodeArgs {
   float out_clamp_lo;
   int out_cells_log2;
   // fast kernel: band layout and 32-bit unit offsets (16 B for BGRA, 4 B for Y / CbCr), see k_encode_fast
-  int tiles_per_row, rps;
+  int tiles_per_row, rps, tile_stride;
   unsigned step_rp, d_rp, pi16, py4, pc4, si16, sy4, sc4, di, dy, dc, wi, wy, wc;
   float one;  // 1.0f, deliberately a runtime value
   unsigned zero;  // 0, deliberately a runtime value (scheduling fence by data dependence, see k_encode_fast)
