@@ -251,6 +251,35 @@ print("bulk ok")
     assert r.returncode == 0 and "bulk ok" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("switch", ["BT709_NO_RING", "BT709_NO_LINEAR", "BT709_NO_COLS2", "BT709_NO_ELOG"])
+def test_superseded_kernel_variants_still_match(switch):
+    """the variants kept for reproduction (band layout, register-prefetch decode, one-column
+    rescale, uniform-cell encode LUT) are selected per process by an environment variable; each must stay exact"""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, "tests")
+from _oracle import Oracle, frame_random, bgra_random
+from _gpu import decode, ctx, dev
+ora = Oracle()
+for (w, h, g) in [(1920, 8, 3), (3840, 4, 2), (640, 6, 0), (2048, 4, 1)]:
+    y, c = frame_random(w, h, seed=6)
+    assert np.array_equal(decode(g, y, c), ora.decode_nv12(g, y, c)), (w, h, g)
+for (iw, ih, ow, oh) in [(192, 108, 256, 144), (300, 200, 150, 100), (64, 64, 64, 64)]:
+    src = bgra_random(iw, ih, seed=7, alpha=None)
+    out = torch.zeros((1, oh, ow, 4), dtype=torch.uint8, device="cuda")
+    ctx().rescale_bgra(dev(src)[None], out, wait=True)
+    assert np.array_equal(out[0].cpu().numpy(), ora.rescale_bgra(src, ow, oh)), (iw, ih, ow, oh)
+print("variant ok")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, **{switch: "1"})
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout + r.stderr
+
+
 def test_padded_frame_strides_take_the_wrap_path():
     """frames separated by padding (frame_stride > rows * pitch): the kernels step across frame seams"""
     from _gpu import ctx
