@@ -13,8 +13,10 @@
 // per pixel off the MUFU pipe and free of shared-memory bank conflicts (per-lane replicated LUT).
 //
 // Kernels (all share decode_row / tile_compute_store):
-//   k_decode_ring     default: per-warp cp.async shared-memory ring for the inputs
-//   k_decode_fast     fallback: per-thread LDG with register prefetch (any 4-byte aligned planes)
+//   k_decode_ring     default: per-warp cp.async shared-memory ring for the inputs; band layout, or linear
+//                     tile order when the tiles per row do not divide the CTA's 32 warps (1920, 3840 wide)
+//   k_decode_fast     fallback: per-thread LDG with register prefetch (any 4-byte aligned planes, ragged and
+//                     2-mod-4 widths, rows wider than 32 tiles)
 //   k_decode_bulk     opt-in (BT709_BULK=1): cp.async.bulk row copies + mbarriers; measured slower
 //   k_decode_generic  any size, pitch and alignment; one thread per 2x2 block
 //
