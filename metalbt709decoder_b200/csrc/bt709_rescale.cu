@@ -459,6 +459,19 @@ __global__ void __launch_bounds__(kWalk2Warps * 32, 1) k_rescale_cols2(const Res
   }
 }
 
+// shared-memory address (low 16 bits matter) at which a kernel's dynamic shared memory starts; -1 = unknown
+static int g_dyn_smem_base = -1;
+__global__ void k_probe_smem_base(unsigned *out) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  *out = (unsigned) __cvta_generic_to_shared(s_mem);
+}
+// dynamic bytes the ELOG layout of walk_tables needs: [LUT, 16 replicas][pad to 64 KB][table 64 KB][row info]
+static size_t elog_layout_bytes(unsigned base, int cells, int warps) {
+  const unsigned head = ((unsigned) cells * 16u + 4u) * 4u;
+  const unsigned pad = head + ((0x10000u - ((base + head) & 0xFFFFu)) & 0xFFFFu);
+  return (size_t) pad + 65536u + (size_t) warps * kWalkRowInfo * 4u;
+}
+
 static size_t walk_smem_bytes(int enc_cells_log2, int rep_log2) {  // 64 KB of alignment slack in front of the table
   return 65536 + (256 * 64 + (size_t) kWalkWarps * kWalkRowInfo + 4 + ((((size_t) 1 << enc_cells_log2) + 1) << rep_log2)) * 4;
 }
@@ -483,8 +496,11 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
       static const bool no_cols2 = getenv("BT709_NO_COLS2") != nullptr;
       static const bool no_elog = getenv("BT709_NO_ELOG") != nullptr;
       const size_t smem_u = walk_smem_bytes(a.enc_cells_log2, 2);  // uniform-cell LUT, 4 replicas
-      // log-cell LUT with 16 replicas: it must end before the 64 KB boundary the table is placed on
-      const bool elog = b.enc_log_lut && !no_elog && (size_t) b.enc_log_cells * 64 + 16 <= 0x1F800;
+      // log-cell LUT with 16 replicas in front of the 64 KB-aligned table: usable when that layout fits the
+      // dynamic shared memory, which depends on where the window starts (probed once, rescale_kernels_init)
+      const bool elog = b.enc_log_lut && !no_elog && g_dyn_smem_base >= 0 &&
+                        elog_layout_bytes((unsigned) g_dyn_smem_base, b.enc_log_cells,
+                                          a.iw <= a.ow && !no_cols2 ? kWalk2Warps : kWalkWarps) <= kMaxDynSmem;
       cudaStream_t st = (cudaStream_t) stream;
       if (a.iw <= a.ow && !no_cols2 && (elog || smem_u <= kMaxDynSmem)) {
         // horizontal scale <= 1: two adjacent columns per thread share their middle texel
@@ -515,6 +531,15 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
 int rescale_kernels_init() {
   const int m = (int) kMaxDynSmem;
   int e;
+  if (g_dyn_smem_base < 0) {  // where does dynamic shared memory start?  (1 KB into the window on sm_100)
+    unsigned *d = nullptr, h = 0;
+    if (cudaMalloc(&d, sizeof(unsigned)) == cudaSuccess) {
+      k_probe_smem_base<<<1, 1, 16>>>(d);
+      if (cudaMemcpy(&h, d, sizeof(unsigned), cudaMemcpyDeviceToHost) == cudaSuccess) g_dyn_smem_base = (int) (h & 0xFFFFu);
+      cudaFree(d);
+    }
+    (void) cudaGetLastError();
+  }
   if ((e = (int) cudaFuncSetAttribute(k_rescale_cols<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, m))) return e;
   if ((e = (int) cudaFuncSetAttribute(k_rescale_cols<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m))) return e;
   if ((e = (int) cudaFuncSetAttribute(k_rescale_cols<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, m))) return e;
