@@ -52,8 +52,8 @@ BT709_API int y4m_write_header(FILE *outFile, Y4MHeaderStruct *hsPtr);
 BT709_API int y4m_write_frame(FILE *outFile, Y4MFrameStruct *fsPtr);
 
 /* Reader.  y4m_read_header parses the stream header (and the reference's XYSCSS line if present) and
- * fills width/height/fps (fps = -1 if the ratio is not one of the enum's); returns 0, or 1 on a
- * malformed header / unsupported chroma format.  y4m_read_frame reads one FRAME into caller buffers of
+ * fills width/height/fps; returns 0, 1 on a malformed header / unsupported chroma format, or 3 when the
+ * frame rate is not one of the enum's (the writer's own bad-fps code).  y4m_read_frame reads one FRAME into caller buffers of
  * w*h, (w/2)*(h/2), (w/2)*(h/2) bytes; returns 0, 1 at end of file, 2 on a truncated frame. */
 BT709_API int y4m_read_header(FILE *inFile, Y4MHeaderStruct *hsPtr);
 BT709_API int y4m_read_frame(FILE *inFile, const Y4MHeaderStruct *hsPtr, uint8_t *y, uint8_t *u, uint8_t *v);

@@ -18,6 +18,8 @@
 
 using namespace bt709;
 
+thread_local unsigned long long bt709::tl_kernel_launches = 0;
+
 struct bt709_ctx {
   int device = -1;
   int sm_count = 148;
@@ -69,9 +71,13 @@ int check_plane(const bt709_plane *p, size_t row_bytes, size_t rows, int nframes
   return BT709_OK;
 }
 
-int finish(const bt709_ctx *ctx, int launch_err, void *stream, int wait) {
+// every launcher call is bracketed by launches_begin() ... finish(): the context counts the kernels really launched
+// (a batch may be split across several launches), not the API calls
+unsigned long long launches_begin() { return tl_kernel_launches; }
+
+int finish(const bt709_ctx *ctx, unsigned long long l0, int launch_err, void *stream, int wait) {
+  ctx->launches.fetch_add(tl_kernel_launches - l0);
   if (launch_err) return cuda_fail(ctx, (cudaError_t) launch_err);
-  ctx->launches.fetch_add(1);
   if (wait) {
     cudaError_t e = cudaStreamSynchronize((cudaStream_t) stream);
     if (e != cudaSuccess) return cuda_fail(ctx, e);
@@ -247,7 +253,8 @@ int bt709_decode_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane
   }
   a.m = ctx->m;
   a.one = 1.0f;
-  return finish(ctx, launch_decode(a, ctx->sm_count, stream), stream, wait);
+  const unsigned long long l0 = launches_begin();
+  return finish(ctx, l0, launch_decode(a, ctx->sm_count, stream), stream, wait);
 }
 
 int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, int in_h, const bt709_plane *out,
@@ -274,7 +281,8 @@ int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, in
   a.enc_log_lut = ctx->dec_log_lut; a.enc_log_clamp_lo = ctx->dec_log_clamp;
   a.enc_log_cells = ctx->dec_log_cells; a.enc_log_first = ctx->dec_log_first;
   a.one = 1.0f;
-  return finish(ctx, launch_rescale(a, ctx->sm_count, stream), stream, wait);
+  const unsigned long long l0 = launches_begin();
+  return finish(ctx, l0, launch_rescale(a, ctx->sm_count, stream), stream, wait);
 }
 
 int bt709_decode_rescale_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y, const bt709_plane *cbcr,
@@ -312,7 +320,8 @@ int bt709_encode_bgra_to_nv12(const bt709_ctx *ctx, bt709_gamma gin, bt709_gamma
   a.lin256 = ctx->lin256[gin];
   a.compn256 = ctx->compn256[gin][gout];
   a.out_lut = ctx->fl_lut[gout]; a.out_clamp_lo = ctx->fl_clamp[gout]; a.out_cells_log2 = ctx->fl_cells[gout];
-  return finish(ctx, launch_encode(a, ctx->sm_count, stream), stream, wait);
+  const unsigned long long l0 = launches_begin();
+  return finish(ctx, l0, launch_encode(a, ctx->sm_count, stream), stream, wait);
 }
 
 int bt709_convert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t *out, int w, int h, void *stream,
@@ -323,7 +332,8 @@ int bt709_convert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t *
   if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
   Packed444Args a{};
   a.in = in; a.out = out; a.n = (long long) w * h; a.enc256 = ctx->enc444_apple; a.m = ctx->m;
-  return finish(ctx, launch_convert444(a, stream), stream, wait);
+  const unsigned long long l0 = launches_begin();
+  return finish(ctx, l0, launch_convert444(a, stream), stream, wait);
 }
 
 int bt709_unconvert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t *out, int w, int h, void *stream,
@@ -335,7 +345,8 @@ int bt709_unconvert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t
   Packed444Args a{};
   a.in = in; a.out = out; a.n = (long long) w * h; a.m = ctx->m;
   a.lut = ctx->dec_lut[kApple]; a.clamp_lo = ctx->dec_clamp[kApple]; a.cells_log2 = ctx->dec_cells[kApple];
-  return finish(ctx, launch_unconvert444(a, stream), stream, wait);
+  const unsigned long long l0 = launches_begin();
+  return finish(ctx, l0, launch_unconvert444(a, stream), stream, wait);
 }
 
 int bt709_copy_packed444_to_nv12(const bt709_ctx *ctx, const uint32_t *in, const bt709_plane *y,
@@ -350,7 +361,8 @@ int bt709_copy_packed444_to_nv12(const bt709_ctx *ctx, const uint32_t *in, const
   CopyPackedArgs a{};
   a.in = in; a.y = (uint8_t *) y->ptr; a.py = (long long) y->pitch; a.c = (uint8_t *) cbcr->ptr;
   a.pc = (long long) cbcr->pitch; a.w = w; a.h = h;
-  return finish(ctx, launch_copy_packed(a, stream), stream, wait);
+  const unsigned long long l0 = launches_begin();
+  return finish(ctx, l0, launch_copy_packed(a, stream), stream, wait);
 }
 
 static int cbcr_planar(const bt709_ctx *ctx, const bt709_plane *cbcr, const bt709_plane *u, const bt709_plane *v, int cw,
@@ -368,7 +380,8 @@ static int cbcr_planar(const bt709_ctx *ctx, const bt709_plane *cbcr, const bt70
   a.u = (uint8_t *) u->ptr; a.pu = (long long) u->pitch; a.su = (long long) u->frame_stride;
   a.v = (uint8_t *) v->ptr; a.pv = (long long) v->pitch; a.sv = (long long) v->frame_stride;
   a.cw = cw; a.ch = ch; a.nframes = nframes;
-  return finish(ctx, launch_cbcr_planar(a, split, stream), stream, wait);
+  const unsigned long long l0 = launches_begin();
+  return finish(ctx, l0, launch_cbcr_planar(a, split, stream), stream, wait);
 }
 
 int bt709_cbcr_to_planar(const bt709_ctx *ctx, const bt709_plane *cbcr, const bt709_plane *u, const bt709_plane *v,

@@ -370,6 +370,132 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
   }
 }
 
+// ================================================================= decode, linear tile stream
+// The kernel for contiguous batches of full tiles (w % 128 == 0, even h, frames back to back): the batch is one
+// tall image, its tiles are numbered row-major and warp g of the grid takes tiles g, g + S, g + 2S, ...  S (the
+// number of participating warps) is rounded DOWN to a multiple of the tiles per row T, so a warp keeps its tile
+// column for the whole kernel and moves S / T row pairs down per step: every pointer advances by a per-lane
+// constant and there is no wrap test, no frame carry and no 32-bit offset limit (at most T - 1 < 32 of the 4736
+// warps idle, against 2 of every 32 in the band layout of 1920- or 3840-wide rows).
+// Same per-warp cp.async ring as k_decode_ring, with the loop overhead cut to the bone (the ring kernel spends
+// ~40 of its ~246 instructions per step on addressing, wrap logic and ring bookkeeping):
+//   * the loop is unrolled over the D ring slots, so slot addresses are immediates;
+//   * ONE __syncwarp per step: the refill of a slot is issued after the barrier of the NEXT step, by which time
+//     every lane has read it;
+//   * all 32 lanes issue the copy; the 8 lanes without a row use a source size of 0 (zero fill into a pad area
+//     of the stage), so the instruction needs no predicate;
+//   * running 64-bit pointers (two adds per step each) instead of offset + wrap + LEA pairs.
+// COMPACT: no pad area in the stage (the 209 KB log-cell LUT of the Linear mode leaves room for 30 compact
+// ring slices); the idle lanes are then predicated off instead.
+template <int CL2, int RL2, bool ALPHA, int D, bool COMPACT>
+__global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
+  extern __shared__ __align__(128) uint32_t s_lut[];
+  constexpr int N = 1 << CL2, R = 1 << RL2;
+  const int entries = CL2 ? N + 1 : p.log_cells;
+  const uint32_t kLutBytes = ((uint32_t) entries * R * 4 + 127u) & ~127u;
+  // Y0 | Y1 | CbCr | pad (| A0 | A1 | pad | pad), 128 B each; COMPACT: without the pads
+  constexpr uint32_t kStage = COMPACT ? (ALPHA ? 640 : 384) : (ALPHA ? 1024 : 512), kAlphaOff = COMPACT ? 384 : 512;
+  for (int i = threadIdx.x; i < entries * R; i += blockDim.x) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_lut);
+  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - ((CL2 ? 0x4B000000u : p.log_first) << (2 + RL2));
+  const uint32_t ring = smem0 + kLutBytes + warp * (D * kStage);
+  const float clamp_lo = p.clamp_lo;
+  DecodeK2 k;
+  k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
+  k.kC = pk(-(8388608.0f + 128.0f), -(8388608.0f + 128.0f));
+  k.inv255 = pk(p.m.inv255, p.m.inv255);
+  k.ys = pk(p.m.ys, p.m.ys);
+  k.g_cb = pk(p.m.g_cb, p.m.g_cb);
+  k.b_cb = pk(p.m.b_cb, p.m.b_cb);
+  k.r_cr = pk(p.m.r_cr, p.m.r_cr);
+  k.g_cr = pk(p.m.g_cr, p.m.g_cr);
+  k.fN = pk((float) N, (float) N);
+  k.magic = pk(8388608.0f, 8388608.0f);
+  k.one = pk(p.one, p.one);
+
+  const unsigned g = blockIdx.x * (unsigned) p.lin_wpc + warp;
+  if (g >= (unsigned) p.lin_warps) return;
+  const unsigned T = (unsigned) p.tiles_per_row, rows2 = (unsigned) p.rows2, drp = (unsigned) p.lin_drp;
+  const unsigned rp0 = g / T, tile = g - rp0 * T;
+  if (rp0 >= rows2) return;
+  const unsigned nsteps = (rows2 - rp0 + drp - 1) / drp;
+
+  // ---- copy role of this lane: lanes 0-7 Y row 0, 8-15 Y row 1, 16-23 the CbCr row, 24-31 zero fill
+  const int role = lane >> 3, sub = lane & 7;
+  const uint8_t *src = role < 2 ? p.y + ((long long) rp0 * 2 + role) * p.py : p.c + (long long) rp0 * p.pc;
+  src += tile * 128 + sub * 16;
+  const long long sinc = role < 2 ? (long long) drp * 2 * p.py : (long long) drp * p.pc;
+  const uint32_t ssize = role < 3 ? 16u : 0u;
+  const uint32_t cdst = ring + role * 128 + sub * 16;
+  // alpha stream (ALPHA only): lanes 0-7 row 0, 8-15 row 1, the rest zero fill
+  const uint8_t *asrc = nullptr;
+  long long ainc = 0;
+  uint32_t asize = 0;
+  if (ALPHA) {
+    asrc = p.a + ((long long) rp0 * 2 + (role & 1)) * p.pa + tile * 128 + sub * 16;
+    ainc = (long long) drp * 2 * p.pa;
+    asize = role < 2 ? 16u : 0u;
+  }
+  auto issue = [&](int slot) {
+    if (COMPACT) {
+      if (role < 3) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cdst + slot * kStage), "l"(src) : "memory");
+    } else {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(cdst + slot * kStage), "l"(src), "r"(ssize) : "memory");
+    }
+    src += sinc;
+    if (ALPHA) {
+      if (COMPACT) {
+        if (role < 2)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(cdst + kAlphaOff + slot * kStage), "l"(asrc) : "memory");
+      } else {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(cdst + kAlphaOff + slot * kStage), "l"(asrc),
+                     "r"(asize)
+                     : "memory");
+      }
+      asrc += ainc;
+    }
+  };
+
+  uint8_t *out0 = p.out + (long long) rp0 * 2 * p.po + (size_t) (tile * 32 + lane) * 16;
+  const long long po = p.po, oinc = (long long) drp * 2 * p.po;
+#pragma unroll
+  for (int j = 0; j < D - 1; j++) {
+    if ((unsigned) j < nsteps) issue(j);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  const uint32_t st0 = ring + lane * 4;
+  for (unsigned kk = 0; kk < nsteps; kk += D) {
+#pragma unroll
+    for (int s = 0; s < D; s++) {
+      if (kk + s >= nsteps) break;  // warp-uniform
+      asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
+      __syncwarp();  // the step's stage is complete for every lane, and every lane is done reading the previous one
+      if (kk + s + D - 1 < nsteps) issue((s + D - 1) % D);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      const uint32_t st = st0 + s * kStage;
+      TileLoad<ALPHA> t;
+      t.y0 = lds_u32(st);
+      t.y1 = lds_u32(st + 128);
+      t.c = lds_u32(st + 256);
+      if (ALPHA) {
+        t.a0 = lds_u32(st + kAlphaOff);
+        t.a1 = lds_u32(st + kAlphaOff + 128);
+      }
+      f32x2 cbn = mul2(add2(pku(magic_byte<0>(t.c), magic_byte<2>(t.c)), k.kC), k.inv255);
+      f32x2 crn = mul2(add2(pku(magic_byte<1>(t.c), magic_byte<3>(t.c)), k.kC), k.inv255);
+      f32x2 cb_g = mul2(cbn, k.g_cb), cb_b = mul2(cbn, k.b_cb);
+      f32x2 cr_r = mul2(crn, k.r_cr), cr_g = mul2(crn, k.g_cr);
+      st_stream_u128(out0, decode_row<CL2, RL2, ALPHA>(t.y0, t.a0, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+      st_stream_u128(out0 + po, decode_row<CL2, RL2, ALPHA>(t.y1, t.a1, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+      out0 += oinc;
+    }
+  }
+}
+
 // ===================================================================== decode, bulk-staged
 // Same arithmetic and the same CTA-band work layout as k_decode_fast, but the input planes reach
 // the SM through the bulk async-copy engine (cp.async.bulk -> UBLKCP, the 1-D TMA path) into a
@@ -681,9 +807,9 @@ static int launch_decode_fast2(const DecodeArgs &a0, int sm_count, cudaStream_t 
       a.linear_tiles = 0;
     }
     if (use_ring)
-      kring<<<grid, kDecodeThreads, smem_ring, s>>>(a);
+      kring<<<grid, kDecodeThreads, smem_ring, s>>>(a), note_launch();
     else
-      k<<<grid, kDecodeThreads, smem, s>>>(a);
+      k<<<grid, kDecodeThreads, smem, s>>>(a), note_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return (int) e;
   }
@@ -709,6 +835,69 @@ static bool bulk_ok(const DecodeArgs &a, int *nstages, int *stage_bytes, int *nr
   if (n < 2) return false;
   *nstages = n;
   return true;
+}
+
+#ifndef BT709_LIN_DEPTH
+#define BT709_LIN_DEPTH 2
+#endif
+constexpr int kLinDepth = BT709_LIN_DEPTH;  // stages of the per-warp cp.async ring of k_decode_lin
+
+// k_decode_lin for a contiguous batch of full tiles (decoded as one tall image).  Returns -1 when it does not apply.
+template <int CL2, int RL2, bool ALPHA, bool COMPACT>
+static int launch_decode_lin(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
+  DecodeArgs a = a0;
+  a.h *= a.nframes;
+  a.rows2 *= a.nframes;
+  a.nframes = 1;
+  const size_t lut_bytes = (((size_t) (CL2 ? (1 << CL2) + 1 : a.log_cells) * (1 << RL2) * 4) + 127) & ~(size_t) 127;
+  if (lut_bytes >= kMaxDynSmem) return -1;
+  const size_t slice = (size_t) kLinDepth * (COMPACT ? (ALPHA ? 640 : 384) : (ALPHA ? 1024 : 512));
+  int wpc = (int) ((kMaxDynSmem - lut_bytes) / slice);
+  if (wpc > 32) wpc = 32;
+  if (wpc < 8) return -1;
+  const unsigned T = (unsigned) a.tiles_per_row;
+  const unsigned long long total_tiles = (unsigned long long) a.rows2 * T;
+  unsigned long long grid = (total_tiles + wpc - 1) / wpc;
+  if (grid > (unsigned long long) sm_count) grid = sm_count;
+  const unsigned W = (unsigned) grid * wpc;
+  if (W < T) return -1;
+  a.lin_wpc = wpc;
+  a.lin_warps = (int) (W / T * T);
+  a.lin_drp = a.lin_warps / (int) T;
+  k_decode_lin<CL2, RL2, ALPHA, kLinDepth, COMPACT><<<(unsigned) grid, wpc * 32, lut_bytes + (size_t) wpc * slice, s>>>(a), note_launch();
+  return (int) cudaGetLastError();
+}
+
+// Picks the k_decode_lin instantiation: per-lane replicated LUT for batches, a few replicas (a much shorter
+// table fill per CTA, some bank conflicts) when the whole call is only a few steps per warp.
+template <bool ALPHA>
+static int try_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s) {
+  static const bool off = getenv("BT709_NO_LIN2") != nullptr;
+  static const char *small_env = getenv("BT709_SMALL_STEPS");
+  static const int small_steps = small_env ? atoi(small_env) : 4;
+  if (off) return -1;
+  if (!((a.w % 128 == 0) && (a.h % 2 == 0))) return -1;
+  const bool contiguous = a.nframes == 1 || (a.sy == (long long) a.h * a.py && a.sc == (long long) a.rows2 * a.pc &&
+                                             a.so == (long long) a.h * a.po && (!ALPHA || a.sa == (long long) a.h * a.pa));
+  if (!contiguous || (long long) a.nframes * a.h >= (1ll << 30)) return -1;
+  if (!(aligned(a.y, 16) && aligned(a.py, 16) && aligned(a.c, 16) && aligned(a.pc, 16) && aligned(a.out, 16) && aligned(a.po, 16) &&
+        (!ALPHA || (aligned(a.a, 16) && aligned(a.pa, 16)))))
+    return -1;
+  // steps per warp with a full grid of 32-warp CTAs
+  const unsigned long long tiles = (unsigned long long) a.nframes * a.rows2 * a.tiles_per_row;
+  const bool small = tiles <= (unsigned long long) small_steps * sm_count * 32;
+  if (a.log_lut && a.log_cells > 0) {
+    DecodeArgs b = a;
+    b.lut = a.log_lut;
+    b.clamp_lo = a.log_clamp_lo;
+    if (small) return launch_decode_lin<0, 2, ALPHA, false>(b, sm_count, s);
+    return launch_decode_lin<0, 5, ALPHA, true>(b, sm_count, s);
+  }
+  if (a.cells_log2 == 10) {
+    if (small) return launch_decode_lin<10, 3, ALPHA, false>(a, sm_count, s);
+    return launch_decode_lin<10, 5, ALPHA, false>(a, sm_count, s);
+  }
+  return -1;
 }
 
 template <int CL2, int RL2, bool ALPHA>
@@ -743,7 +932,7 @@ static int launch_decode_fast(const DecodeArgs &a0, int sm_count, cudaStream_t s
       a.po16 = (unsigned) (a.po / 16); a.so16 = (unsigned) (a.so / 16);
       a.dout = d_f * a.so16 + a.d_rp * 2 * a.po16;
       a.wout = a.so16 - a.rows2 * 2 * a.po16;
-      k_decode_bulk<CL2, RL2, ALPHA, kDecodeThreads><<<grid, kDecodeThreads, smem, s>>>(a);
+      k_decode_bulk<CL2, RL2, ALPHA, kDecodeThreads><<<grid, kDecodeThreads, smem, s>>>(a), note_launch();
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return (int) e;
     }
@@ -793,6 +982,10 @@ int launch_decode(const DecodeArgs &a0, int sm_count, void *stream) {
               (a.cells_log2 == 10 || a.cells_log2 == 12);
   if (alpha) fast = fast && aligned(a.a, 4) && aligned(a.pa, 4) && aligned(a.sa, 4);
   if (fast) {
+    {
+      const int e = alpha ? try_decode_lin<true>(a, sm_count, s) : try_decode_lin<false>(a, sm_count, s);
+      if (e != -1) return e;  // -1: not applicable, use the older kernels below
+    }
     // Linear mode: the steep pure-sRGB-encode step function needs 4096 uniform cells (8 replicas, 2-3 way
     // bank conflicts) but only ~1650 log-spaced ones, which fit shared memory with one replica per lane
     if (a.log_lut && a.log_cells > 0 && (size_t) a.log_cells * 128 <= kMaxDynSmem) {
@@ -808,9 +1001,9 @@ int launch_decode(const DecodeArgs &a0, int sm_count, void *stream) {
   long long grid = (blocks + 255) / 256;
   if (grid > (long long) sm_count * 16) grid = (long long) sm_count * 16;
   if (alpha)
-    k_decode_generic<true><<<(unsigned) grid, 256, 0, s>>>(a);
+    k_decode_generic<true><<<(unsigned) grid, 256, 0, s>>>(a), note_launch();
   else
-    k_decode_generic<false><<<(unsigned) grid, 256, 0, s>>>(a);
+    k_decode_generic<false><<<(unsigned) grid, 256, 0, s>>>(a), note_launch();
   return (int) cudaGetLastError();
 }
 
@@ -827,6 +1020,18 @@ static int optin_decode_smem_log() {
   if (e) return e;
   e = (int) cudaFuncSetAttribute(k_decode_ring<0, 5, ALPHA, true, kRingDepth, kDecodeThreads>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<0, 5, ALPHA, kLinDepth, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<0, 2, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<10, 5, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<10, 3, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
   if (e) return e;
   return (int) cudaFuncSetAttribute(k_decode_ring<0, 5, ALPHA, false, kRingDepth, kDecodeThreads>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);

@@ -282,7 +282,37 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   }
 }
 
+static int launch_encode_fast1(const EncodeArgs &a0, int sm_count, cudaStream_t s);
+
+// Every plane is addressed with 32-bit unit offsets (16 B for BGRA, 4 B for Y / CbCr): split the batch by frames so
+// that no offset of any of the three planes reaches 2^32 (padded output frame strides can get there long before
+// the input does), like the decode launcher.
 static int launch_encode_fast(const EncodeArgs &a0, int sm_count, cudaStream_t s) {
+  const unsigned long long lim = 0xFFFF0000ull;
+  unsigned long long per = lim;
+  auto fit = [&](long long stride, unsigned unit, long long frame_bytes) {
+    if (stride <= 0 || a0.nframes == 1) return;
+    if ((unsigned long long) frame_bytes >= lim * unit) { per = 1; return; }
+    unsigned long long n = (lim * unit - (unsigned long long) frame_bytes) / (unsigned long long) stride + 1;
+    if (n < per) per = n;
+  };
+  fit(a0.si, 16, (long long) a0.h * a0.pi);
+  fit(a0.sy, 4, (long long) a0.h * a0.py);
+  fit(a0.sc, 4, (long long) (a0.h / 2) * a0.pc);
+  if (per < 1) per = 1;
+  for (long long f0 = 0; f0 < a0.nframes; f0 += (long long) per) {
+    EncodeArgs a = a0;
+    a.nframes = (int) ((unsigned long long) (a0.nframes - f0) < per ? (unsigned long long) (a0.nframes - f0) : per);
+    a.in = a0.in + f0 * a0.si;
+    a.y = a0.y + f0 * a0.sy;
+    a.c = a0.c + f0 * a0.sc;
+    int e = launch_encode_fast1(a, sm_count, s);
+    if (e) return e;
+  }
+  return 0;
+}
+
+static int launch_encode_fast1(const EncodeArgs &a0, int sm_count, cudaStream_t s) {
   EncodeArgs a = a0;
   const int rows2 = a.h / 2;
   const int wpc = 32;
@@ -312,8 +342,8 @@ static int launch_encode_fast(const EncodeArgs &a0, int sm_count, cudaStream_t s
   const bool wide = a.tiles_per_row > wpc || wpc % a.tiles_per_row == 0;
 #define BT709_ENC_LAUNCH(W, F)                                                      \
   do {                                                                              \
-    if (wide) k_encode_fast<W, F, true><<<grid, 1024, smem, s>>>(a);                \
-    else k_encode_fast<W, F, false><<<grid, 1024, smem, s>>>(a);                    \
+    if (wide) k_encode_fast<W, F, true><<<grid, 1024, smem, s>>>(a), note_launch();                \
+    else k_encode_fast<W, F, false><<<grid, 1024, smem, s>>>(a), note_launch();                    \
   } while (0)
   if (wrap) {
     if (full) BT709_ENC_LAUNCH(true, true); else BT709_ENC_LAUNCH(true, false);
@@ -332,17 +362,19 @@ int launch_encode(const EncodeArgs &a, int sm_count, void *stream) {
   const bool vec = (a.w % 4 == 0) && aligned(a.in, 16) && aligned(a.pi, 16) && aligned(a.si, 16) && aligned(a.y, 4) &&
                    aligned(a.py, 4) && aligned(a.sy, 4) && aligned(a.c, 4) && aligned(a.pc, 4) && aligned(a.sc, 4);
   // fast path: aligned planes (any even width), offsets that fit 32-bit units
-  const unsigned long long in_bytes = (unsigned long long) a.nframes * (a.si > 0 ? a.si : (long long) a.h * a.pi);
-  if (al && in_bytes < 0xFFFF0000ull * 16 && a.si >= 0 && a.sy >= 0 && a.sc >= 0 &&
-      a.out_cells_log2 <= 12)
+  // (one frame must fit the 32-bit unit offsets of every plane; batches are split by frames in launch_encode_fast)
+  const unsigned long long lim = 0xFFFF0000ull;
+  const bool frame_fits = (unsigned long long) a.h * a.pi < lim * 16 && (unsigned long long) a.h * a.py < lim * 4 &&
+                          (unsigned long long) (a.h / 2) * a.pc < lim * 4;
+  if (al && frame_fits && a.si >= 0 && a.sy >= 0 && a.sc >= 0 && a.out_cells_log2 <= 12)
     return launch_encode_fast(a, sm_count, s);
   const long long n = (long long) a.nframes * (a.h / 2) * (vec ? a.w / 4 : a.w / 2);
   long long grid = (n + 255) / 256;
   if (grid > (long long) sm_count * 8) grid = (long long) sm_count * 8;
   if (vec)
-    k_encode<true><<<(unsigned) grid, 256, smem, s>>>(a);
+    k_encode<true><<<(unsigned) grid, 256, smem, s>>>(a), note_launch();
   else
-    k_encode<false><<<(unsigned) grid, 256, smem, s>>>(a);
+    k_encode<false><<<(unsigned) grid, 256, smem, s>>>(a), note_launch();
   return (int) cudaGetLastError();
 }
 

@@ -69,11 +69,18 @@ struct Guard {
 // pick the stream + staging slot for one call.  With a caller stream the slot's buffers are
 // still used, ordered after the slot's previous work by an event wait on the device.
 Slot *acquire(MetalRenderContext *mrc, void *commandBuffer, cudaStream_t *stream) {
-  std::lock_guard<std::mutex> lk(mrc->mu);
-  Slot *s = &mrc->slots[mrc->next];
-  mrc->next = (mrc->next + 1) % kSlots;
+  Slot *s;
+  {
+    std::lock_guard<std::mutex> lk(mrc->mu);
+    s = &mrc->slots[mrc->next];
+    mrc->next = (mrc->next + 1) % kSlots;
+  }
+  s->busy.lock();  // released by finish(); more than kSlots concurrent callers queue up here
   *stream = commandBuffer ? (cudaStream_t) commandBuffer : s->stream;
-  if (commandBuffer) cudaStreamWaitEvent(*stream, s->done, 0);
+  // Always order this call after the slot's previous work: the previous call may have run on a caller stream
+  // (or this one does), and the staging buffers are shared.  A wait on an event recorded on the same stream, or
+  // never recorded, is a no-op.
+  cudaStreamWaitEvent(*stream, s->done, 0);
   return s;
 }
 
@@ -86,6 +93,7 @@ bool download2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t
 
 bool finish(Slot *s, cudaStream_t st, bool ok, int wait) {
   cudaEventRecord(s->done, st);
+  s->busy.unlock();
   if (!ok) {
     cudaGetLastError();
     return false;
@@ -170,13 +178,28 @@ MetalRenderContext *MetalRenderContext_new(int device) {
 
 int MetalRenderContext_setupMetal(MetalRenderContext *mrc) {
   if (!mrc) return 0;
+  std::lock_guard<std::mutex> lk(mrc->mu);  // may be called from any thread
   if (mrc->ctx) return 1;  // idempotent, as in the reference
-  if (bt709_ctx_create(mrc->device, &mrc->ctx) != BT709_OK) return 0;
+  bt709_ctx *ctx = nullptr;
+  if (bt709_ctx_create(mrc->device, &ctx) != BT709_OK) return 0;
   Guard g(mrc->device);
-  for (int i = 0; i < kSlots; i++) {
-    if (cudaStreamCreateWithFlags(&mrc->slots[i].stream, cudaStreamNonBlocking) != cudaSuccess) return 0;
-    if (cudaEventCreateWithFlags(&mrc->slots[i].done, cudaEventDisableTiming) != cudaSuccess) return 0;
+  bool ok = true;
+  for (int i = 0; i < kSlots && ok; i++) {
+    ok = cudaStreamCreateWithFlags(&mrc->slots[i].stream, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&mrc->slots[i].done, cudaEventDisableTiming) == cudaSuccess;
   }
+  if (!ok) {  // tear down the partial setup; the context is published only when everything exists
+    for (int i = 0; i < kSlots; i++) {
+      if (mrc->slots[i].done) cudaEventDestroy(mrc->slots[i].done);
+      if (mrc->slots[i].stream) cudaStreamDestroy(mrc->slots[i].stream);
+      mrc->slots[i].done = nullptr;
+      mrc->slots[i].stream = nullptr;
+    }
+    cudaGetLastError();
+    bt709_ctx_destroy(ctx);
+    return 0;
+  }
+  mrc->ctx = ctx;
   return 1;
 }
 

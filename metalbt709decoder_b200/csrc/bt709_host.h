@@ -23,6 +23,7 @@ constexpr int kSlots = 4;  // frames in flight: upload of frame i+1 overlaps rea
 struct Slot {
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  std::mutex busy;  // held from acquire() to finish(): one thread at a time enqueues on a slot's buffers
   DevBuf y, c, a, out, mid, in;
 };
 

@@ -14,7 +14,7 @@ struct DecodeArgs {
   long long sy, sc, sa, so;  // frame strides, bytes
   int w, h, nframes;
   int rows2;            // ceil(h / 2) row pairs per frame
-  int tiles_per_row;    // 256-pixel tiles per row pair (fast kernel)
+  int tiles_per_row;    // 128-pixel tiles per row pair (fast kernels)
   int rps;              // row pairs a CTA covers per step = 32 / tiles_per_row (>= 1)
   int tile_stride;      // min(tiles_per_row, 32): warps loop over tiles when a row has more than 32
   // fast kernel addressing: 32-bit offsets in load/store units (4 B for Y/CbCr/alpha, 16 B for BGRA)
@@ -28,6 +28,10 @@ struct DecodeArgs {
   // take 32 consecutive tiles of the row-major tile sequence; the per-step increments step the tile COLUMN and
   // the wrap increments fire when the column passes the end of the row (same code as the frame wrap).
   int linear_tiles;
+  // k_decode_lin (contiguous full-tile batches): the batch is one tall image whose 128-pixel x 2-row tiles are
+  // taken in row-major order by `lin_warps` warps (a multiple of the tiles per row, so a warp keeps its tile
+  // column for the whole kernel and steps `lin_drp` row pairs down per step: no wrap logic, constant strides)
+  int lin_warps, lin_drp, lin_wpc;      // active warps in the grid; row pairs per step; warps per CTA
   // bulk-staged kernel: shared-memory ring geometry
   int nstages, stage_bytes, nrows;      // ring depth; bytes per stage; rows (= bulk copies) per stage
   const uint32_t *lut;  // cell LUT of the selected gamma, N + 1 words, device memory
@@ -100,6 +104,10 @@ struct PlanarArgs {
   long long pc, pu, pv, sc, su, sv;
   int cw, ch, nframes;
 };
+
+// number of kernels the calling thread has launched through the launchers below (bt709_launch_count accounting)
+extern thread_local unsigned long long tl_kernel_launches;
+inline void note_launch() { ++tl_kernel_launches; }
 
 // launchers (one per kernel family).  Each returns the cudaError_t of the launch.
 int launch_decode(const DecodeArgs &a, int sm_count, void *stream);

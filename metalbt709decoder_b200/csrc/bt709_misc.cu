@@ -80,9 +80,9 @@ int launch_cbcr_planar(const PlanarArgs &a, bool split, void *stream) {
   long long g = (n + 255) / 256;
   g = g > 148 * 16 ? 148 * 16 : (g < 1 ? 1 : g);
   if (split)
-    k_cbcr_planar<true><<<(unsigned) g, 256, 0, (cudaStream_t) stream>>>(a);
+    k_cbcr_planar<true><<<(unsigned) g, 256, 0, (cudaStream_t) stream>>>(a), note_launch();
   else
-    k_cbcr_planar<false><<<(unsigned) g, 256, 0, (cudaStream_t) stream>>>(a);
+    k_cbcr_planar<false><<<(unsigned) g, 256, 0, (cudaStream_t) stream>>>(a), note_launch();
   return (int) cudaGetLastError();
 }
 
@@ -92,15 +92,15 @@ static unsigned grid_1d(long long n) {
 }
 
 int launch_convert444(const Packed444Args &a, void *stream) {
-  k_convert444<<<grid_1d(a.n), 256, 0, (cudaStream_t) stream>>>(a);
+  k_convert444<<<grid_1d(a.n), 256, 0, (cudaStream_t) stream>>>(a), note_launch();
   return (int) cudaGetLastError();
 }
 int launch_unconvert444(const Packed444Args &a, void *stream) {
-  k_unconvert444<<<grid_1d(a.n), 256, 0, (cudaStream_t) stream>>>(a);
+  k_unconvert444<<<grid_1d(a.n), 256, 0, (cudaStream_t) stream>>>(a), note_launch();
   return (int) cudaGetLastError();
 }
 int launch_copy_packed(const CopyPackedArgs &a, void *stream) {
-  k_copy_packed<<<grid_1d((long long) a.w * a.h), 256, 0, (cudaStream_t) stream>>>(a);
+  k_copy_packed<<<grid_1d((long long) a.w * a.h), 256, 0, (cudaStream_t) stream>>>(a), note_launch();
   return (int) cudaGetLastError();
 }
 

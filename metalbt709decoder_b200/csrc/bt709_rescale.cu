@@ -507,14 +507,14 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
         const long long tiles64 = (long long) ((a.ow + 63) / 64) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
         const long long ctas2 = (tiles64 + kWalk2Warps - 1) / kWalk2Warps;
         const unsigned g2 = (unsigned) (ctas2 < (long long) sm_count ? ctas2 : (long long) sm_count);
-        if (elog) k_rescale_cols2<4, true><<<g2, kWalk2Warps * 32, kMaxDynSmem, st>>>(b);
-        else k_rescale_cols2<2, false><<<g2, kWalk2Warps * 32, smem_u, st>>>(b);
+        if (elog) k_rescale_cols2<4, true><<<g2, kWalk2Warps * 32, kMaxDynSmem, st>>>(b), note_launch();
+        else k_rescale_cols2<2, false><<<g2, kWalk2Warps * 32, smem_u, st>>>(b), note_launch();
       } else if (elog) {
-        k_rescale_cols<4, true><<<grid2, kWalkWarps * 32, kMaxDynSmem, st>>>(b);
+        k_rescale_cols<4, true><<<grid2, kWalkWarps * 32, kMaxDynSmem, st>>>(b), note_launch();
       } else if (smem_u <= kMaxDynSmem) {
-        k_rescale_cols<2, false><<<grid2, kWalkWarps * 32, smem_u, st>>>(b);
+        k_rescale_cols<2, false><<<grid2, kWalkWarps * 32, smem_u, st>>>(b), note_launch();
       } else {
-        k_rescale_cols<0, false><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 0), st>>>(b);
+        k_rescale_cols<0, false><<<grid2, kWalkWarps * 32, walk_smem_bytes(a.enc_cells_log2, 0), st>>>(b), note_launch();
       }
       cudaError_t e = cudaGetLastError();
       if (e != cudaSuccess) return (int) e;
@@ -524,7 +524,7 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
   const size_t smem = (256 + (size_t) (1 << a.enc_cells_log2) + 1) * 4;
   const long long tiles = (long long) a.nframes * ((a.ow + 31) / 32) * ((a.oh + 7) / 8);
   long long grid = tiles < (long long) sm_count * 8 ? tiles : (long long) sm_count * 8;
-  k_rescale<<<(unsigned) grid, 256, smem, (cudaStream_t) stream>>>(a);
+  k_rescale<<<(unsigned) grid, 256, smem, (cudaStream_t) stream>>>(a), note_launch();
   return (int) cudaGetLastError();
 }
 

@@ -89,6 +89,7 @@ int y4m_read_header(FILE *in, Y4MHeaderStruct *hs) {
                                              {25, 1, Y4MHeaderFPS_25}, {30000, 1001, Y4MHeaderFPS_29_97},
                                              {30, 1, Y4MHeaderFPS_30}, {60, 1, Y4MHeaderFPS_60}};
   for (const auto &t : tab) if (t.n == num && t.d == den) fps = t.e;
+  if (fps < 0) return 3;  // a frame rate the writer's enum cannot express (same code as y4m_write_header's bad fps)
   hs->fps = (Y4MHeaderFPS) fps;
   // the reference's stray comment line, if this file came from its writer
   long at = ftell(in);

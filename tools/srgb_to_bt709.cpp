@@ -64,6 +64,7 @@ static bool decode_png(const std::vector<uint8_t> &d, Image *img) {
     if (pos + 12 + len > d.size()) return false;
     const uint8_t *body = &d[pos + 8];
     if (!memcmp(type, "IHDR", 4)) {
+      if (len != 13) return false;  // a short IHDR would be read past its end
       w = (int) be32(body); h = (int) be32(body + 4); depth = body[8]; ctype = body[9]; interlace = body[12];
     } else if (!memcmp(type, "IDAT", 4)) {
       idat.insert(idat.end(), body, body + len);
@@ -75,6 +76,11 @@ static bool decode_png(const std::vector<uint8_t> &d, Image *img) {
   int ch = ctype == 0 ? 1 : ctype == 2 ? 3 : ctype == 4 ? 2 : ctype == 6 ? 4 : 0;
   if (w <= 0 || h <= 0 || depth != 8 || ch == 0 || interlace != 0) {
     fprintf(stderr, "unsupported PNG (need 8-bit gray/RGB/RGBA, non-interlaced, not indexed)\n");
+    return false;
+  }
+  // sanity bound before allocating from header fields (16384 x 16384 is far beyond any frame this tool converts)
+  if (w > 16384 || h > 16384) {
+    fprintf(stderr, "unsupported PNG (dimensions %d x %d too large)\n", w, h);
     return false;
   }
   const size_t stride = (size_t) w * ch;
