@@ -2,7 +2,8 @@
 """bench.py — headline benchmark of the BT.709 4:2:0 -> sRGB BGRA8 decode path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
-                    [--workload c2_1080p|c3_uhd|c2_rescale|c4_alpha|c5_encode] [--gamma bt709|apple|srgb|linear]
+                    [--workload c2_1080p|c3_uhd|c2_rescale|c2_twopass|c2_fused|c4_alpha|c5_encode]
+                    [--gamma bt709|apple|srgb|linear] [--no-configs] [--no-e2e]
 
 Metric (BASELINE.json): Gpix/s of BT.709 4:2:0 -> sRGB BGRA8, plus % of the HBM roofline.
 A "step" is one pass of the hot path over one resident batch of synthetic frames (configs[1]:
@@ -11,8 +12,13 @@ needed between steps).  `value` counts pixels of all ranks / max-over-ranks devi
 Multi-GPU: one process per GPU (torchrun), frames sharded by index, no data-path collective;
 torch.distributed is used only for the barrier and for reducing the timing scalars.
 
+The JSON line also carries `configs`: every other BASELINE configuration (UHD batch, RGB + alpha, pass 2 alone,
+two-pass and fused decode -> rescale, the 4:2:0 encode) timed in the same run, each with its own value,
+roofline fraction and clock record (single-GPU runs only; --no-configs skips them).
+
 `e2e` is the same metric through the reference-facing host API (MetalBT709Decoder_decodeBT709
-with pinned HOST buffers): upload, kernel and read-back are all inside the timed region.
+with pinned HOST buffers): upload, kernel and read-back are all inside the timed region; its output is
+compared with the device-resident kernel's output for the same frames.
 
 --impl reference times the reference's own CPU implementation of the path (oracle/_ref: the
 unmodified BT709.h compiled where it lies; else the oracle port) on the host cores.
@@ -28,14 +34,24 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+OUT_W, OUT_H = 2560, 1440  # pass-2 target of configs[1]
 WORKLOADS = {
     # name: (w, h, frames per GPU, kind)
     "c2_1080p": (1920, 1080, 600, "decode"),
     "c3_uhd": (3840, 2160, 300, "decode"),       # 2400 frames / 8 GPUs per BASELINE configs[2]
     "c2_rescale": (1920, 1080, 200, "rescale"),  # pass 2 alone, 1080p -> 2560x1440
-    "c2_twopass": (1920, 1080, 200, "twopass"),  # decode -> intermediate -> rescale
+    "c2_twopass": (1920, 1080, 200, "twopass"),  # decode -> same-size intermediate in HBM -> rescale (two launches)
+    "c2_fused": (1920, 1080, 200, "fused"),      # bt709_decode_rescale_nv12: one kernel, no intermediate
     "c4_alpha": (2048, 1536, 200, "alpha"),
     "c5_encode": (2048, 1536, 200, "encode"),
+}
+KIND_TEXT = {
+    "decode": "NV12 video-range frames -> sRGB BGRA8 (decode, pass 1)",
+    "alpha": "RGB NV12 + alpha-stream Y plane -> BGRA8 with A (decode, sRGB gamma forced)",
+    "rescale": f"sRGB BGRA8 frames -> {OUT_W}x{OUT_H} (pass 2 alone, bilinear in linear light)",
+    "twopass": f"NV12 frames -> sRGB BGRA8 intermediate -> {OUT_W}x{OUT_H} (decode + rescale, two launches)",
+    "fused": f"NV12 frames -> {OUT_W}x{OUT_H} sRGB BGRA8 (fused decode -> rescale, one launch)",
+    "encode": "sRGB BGRA8 frames -> NV12 video-range (4:2:0 encode, sRGB in / Apple out)",
 }
 GAMMAS = {"apple": 0, "srgb": 1, "linear": 2, "bt709": 3}
 
@@ -169,11 +185,30 @@ def cpu_baseline(gamma, w, h, budget_core_s=16.0):
             "sample": f"{nframes} synthetic {w}x{h} frames, one frame per task on {cores} host threads"}, secs
 
 
+def workload_text(name, frames, gamma_name):
+    w, h, _, kind = WORKLOADS[name]
+    g = "srgb" if kind == "alpha" else gamma_name
+    extra = "" if kind in ("rescale", "encode") else f", gamma={g}"
+    return f"{name}: {frames} x {w}x{h} {KIND_TEXT[kind]}{extra}"
+
+
+def config_of(args, frames, world, fps=None):
+    """The `config` object of the JSON line; the reference arm prints the SAME object for the same arguments."""
+    c = {"workload": workload_text(args.workload, frames, args.gamma), "frames_per_gpu": frames,
+         "l2": "inputs+outputs per step >> 126 MB L2; no flush needed",
+         "parallelism": f"frame-sharded x{world}, no collective"}
+    if fps is not None:
+        c["fps"] = fps
+    return c
+
+
 def run_reference(args):
     rank, _, world = _dist_env()
     if rank != 0:
         return 0
     w, h, frames, kind = WORKLOADS[args.workload]
+    if args.frames:
+        frames = args.frames
     gamma = GAMMAS[args.gamma]
     cores = os.cpu_count() or 1
     per_step = max(cores, min(cores * 2, 256))
@@ -185,14 +220,15 @@ def run_reference(args):
         s, kind_impl = _cpu_decode_frames(gamma, w, h, per_step, cores)
         t += s
     value = per_step * args.steps * w * h / t / 1e9
-    sample = f"{per_step} synthetic {w}x{h} frames per step, one frame per task on {cores} host threads"
+    sample = (f"{per_step} synthetic {w}x{h} frames per step (a bounded sample of the {frames}-frame batch), "
+              f"one frame per task on {cores} host threads")
     line = {
         "impl": "reference", "metric": "Gpix/s BT.709 4:2:0->sRGB BGRA8", "value": value, "unit": "Gpix/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (double pow), u8 I/O",
         "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {w}x{h} NV12 video-range -> sRGB BGRA8, gamma={args.gamma}",
-                   "frames_per_step": per_step, "note": "reference CPU path on host cores; bounded sample"},
+        "config": config_of(args, frames, max(1, world)),
+        "note": "reference CPU path (BT709.h / sRGB.h) on the host cores; each step is a bounded sample of the workload",
         "cpu_baseline": {"value": value, "unit": "Gpix/s", "cores": cores, "kind": kind_impl, "sample": sample},
         "e2e": {"value": value, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -207,16 +243,18 @@ def make_batch(torch, w, h, frames, seed, kind):
     g = torch.Generator(device="cuda")
     g.manual_seed(seed)
     d = {}
-    if kind in ("decode", "alpha", "twopass"):
+    if kind in ("decode", "alpha", "twopass", "fused"):
         d["y"] = torch.randint(16, 236, (frames, h, w), dtype=torch.uint8, device="cuda", generator=g)
         d["c"] = torch.randint(16, 241, (frames, h // 2, w), dtype=torch.uint8, device="cuda", generator=g)
+    if kind in ("decode", "alpha", "twopass"):
         d["out"] = torch.empty((frames, h, w, 4), dtype=torch.uint8, device="cuda")
     if kind == "alpha":
         d["a"] = torch.randint(16, 236, (frames, h, w), dtype=torch.uint8, device="cuda", generator=g)
-    if kind in ("rescale", "twopass"):
+    if kind in ("rescale", "twopass", "fused"):
         if kind == "rescale":
             d["src"] = torch.randint(0, 256, (frames, h, w, 4), dtype=torch.uint8, device="cuda", generator=g)
-        d["big"] = torch.empty((frames, 1440, 2560, 4), dtype=torch.uint8, device="cuda")
+            d["src"][..., 3] = 255  # what pass 1 hands over for opaque video (AAPLShaders.metal:243)
+        d["big"] = torch.empty((frames, OUT_H, OUT_W, 4), dtype=torch.uint8, device="cuda")
     if kind == "encode":
         d["src"] = torch.randint(0, 256, (frames, h, w, 4), dtype=torch.uint8, device="cuda", generator=g)
         d["y"] = torch.empty((frames, h, w), dtype=torch.uint8, device="cuda")
@@ -225,7 +263,9 @@ def make_batch(torch, w, h, frames, seed, kind):
 
 
 def algorithmic_bytes(kind, w, h, frames):
+    """bytes the workload has to move per step, independent of how a kernel moves them."""
     px = w * h * frames
+    opx = OUT_W * OUT_H * frames
     if kind == "decode":
         return 5.5 * px
     if kind == "alpha":
@@ -233,10 +273,82 @@ def algorithmic_bytes(kind, w, h, frames):
     if kind == "encode":
         return 5.5 * px
     if kind == "rescale":
-        return 4.0 * px + 4.0 * 2560 * 1440 * frames
+        return 4.0 * px + 4.0 * opx
     if kind == "twopass":
-        return 5.5 * px + 4.0 * px + 4.0 * 2560 * 1440 * frames
+        return 5.5 * px + 4.0 * px + 4.0 * opx
+    if kind == "fused":
+        return 1.5 * px + 4.0 * opx
     raise ValueError(kind)
+
+
+def make_step(ctx, d, kind, gamma, stream):
+    if kind == "decode":
+        return lambda: ctx.decode_nv12(gamma, d["y"], d["c"], d["out"], stream=stream)
+    if kind == "alpha":
+        return lambda: ctx.decode_nv12(1, d["y"], d["c"], d["out"], alpha_y=d["a"], stream=stream)
+    if kind == "rescale":
+        return lambda: ctx.rescale_bgra(d["src"], d["big"], stream=stream)
+    if kind == "twopass":
+        def two():
+            ctx.decode_nv12(gamma, d["y"], d["c"], d["out"], stream=stream)
+            ctx.rescale_bgra(d["out"], d["big"], stream=stream)
+        return two
+    if kind == "fused":
+        return lambda: ctx.decode_rescale_nv12(gamma, d["y"], d["c"], None, d["big"], stream=stream)
+    if kind == "encode":
+        return lambda: ctx.encode_bgra_to_nv12(1, 0, d["src"], d["y"], d["c"], stream=stream)
+    raise ValueError(kind)
+
+
+def roofline_of(kind, w, h, frames, avg_step_s, launches_per_step):
+    peak, peak_src = measured_peak_gbs()
+    ach = algorithmic_bytes(kind, w, h, frames) / avg_step_s / 1e9
+    return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "traffic": ncu_traffic(kind, float(frames) * w * h / launches_per_step), "peak_source": peak_src,
+            "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per pixel of the "
+                              "committed `ncu --set full` capture of this kernel, scaled to this launch",
+            "algorithmic_bytes_per_launch": algorithmic_bytes(kind, w, h, frames) / launches_per_step,
+            "avg_launch_ms": avg_step_s * 1e3 / launches_per_step, "kernels_per_step": launches_per_step}
+
+
+def run_extra_config(torch, ctx, name, gamma, gamma_name, device_index, min_seconds=0.35):
+    """One of the other BASELINE configurations, timed in the same run: >= 20 steps and >= min_seconds of device
+    time so that the clock sampler sees it."""
+    w, h, frames, kind = WORKLOADS[name]
+    stream = torch.cuda.current_stream()
+    d = make_batch(torch, w, h, frames, 709, kind)
+    step = make_step(ctx, d, kind, gamma, stream)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for _ in range(3):
+        step()
+    e0.record(stream)
+    for _ in range(3):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    est = e0.elapsed_time(e1) / 3e3
+    steps = int(min(400, max(20, min_seconds / max(est, 1e-6))))
+    sampler = ClockSampler(device_index)
+    sampler.start()
+    n0 = ctx.launch_count
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    launches = ctx.launch_count - n0
+    clocks = sampler.stop()
+    secs = e0.elapsed_time(e1) / 1e3
+    px = float(frames) * w * h * steps
+    lps = max(1, launches // steps)
+    out = {"name": name, "workload": workload_text(name, frames, gamma_name), "value": px / secs / 1e9, "unit": "Gpix/s",
+           "value_basis": "input pixels", "fps": frames * steps / secs, "steps": steps, "warmup": 6,
+           "ms_per_step": secs / steps * 1e3, "roofline": roofline_of(kind, w, h, frames, secs / steps, lps),
+           "gpu_launches": launches, "clocks": clocks}
+    del d
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_b200(args):
@@ -263,18 +375,7 @@ def run_b200(args):
     ctx = pkg.BT709Context(local_rank)
     d = make_batch(torch, w, h, frames, 709 + lo, kind)
     stream = torch.cuda.current_stream()
-
-    def step():
-        if kind == "decode":
-            ctx.decode_nv12(gamma, d["y"], d["c"], d["out"], stream=stream)
-        elif kind == "alpha":
-            ctx.decode_nv12(gamma, d["y"], d["c"], d["out"], alpha_y=d["a"], stream=stream)
-        elif kind == "rescale":
-            ctx.rescale_bgra(d["src"], d["big"], stream=stream)
-        elif kind == "twopass":
-            ctx.decode_rescale_nv12(gamma, d["y"], d["c"], d["out"], d["big"], stream=stream)
-        elif kind == "encode":
-            ctx.encode_bgra_to_nv12(1, 0, d["src"], d["y"], d["c"], stream=stream)
+    step = make_step(ctx, d, kind, gamma, stream)
 
     def barrier():
         if world > 1:
@@ -298,60 +399,69 @@ def run_b200(args):
     launches = ctx.launch_count - n0
     clocks = sampler.stop() if rank == 0 else None
     total_ms = evs[0].elapsed_time(evs[-1])
-    per_launch_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
+    per_step_ms = [evs[i].elapsed_time(evs[i + 1]) for i in range(args.steps)]
     units = float(frames) * w * h * args.steps
     secs, all_units = gather_job_stats(total_ms / 1e3, units)
 
     # ---- end-to-end through the reference-facing host API (host buffers, copies timed)
     e2e = None
     if kind == "decode" and not args.no_e2e:
-        e2e = run_e2e(args, local_rank, w, h, frames, gamma)
+        e2e = run_e2e(args, ctx, local_rank, w, h, frames, gamma)
         if world > 1:
             e_secs, e_units = gather_job_stats(e2e["_secs"], e2e["_units"])
         else:
             e_secs, e_units = e2e["_secs"], e2e["_units"]
         e2e = {"value": e_units / e_secs / 1e9, "unit": "Gpix/s", "h2d_bytes_per_step": e2e["h2d"],
                "d2h_bytes_per_step": e2e["d2h"], "frames_per_step": e2e["frames"], "steps": e2e["steps"],
-               "api": "MetalBT709Decoder_decodeBT709 (pinned host NV12 in, pinned host BGRA out, 4-deep stream ring)"}
+               "gamma": e2e["gamma"], "verified": e2e["verified"],
+               "api": "MetalBT709Decoder_decodeBT709 (pinned host NV12 in, pinned host BGRA out, one frame per call, "
+                      "4-deep stream ring)"}
+
+    # ---- the other BASELINE configurations, same run (single GPU only)
+    configs = None
+    if world == 1 and not args.no_configs:
+        del d
+        torch.cuda.empty_cache()
+        configs = []
+        for name in ("c3_uhd", "c4_alpha", "c2_rescale", "c2_twopass", "c2_fused", "c5_encode", "c2_1080p"):
+            if name == args.workload:
+                continue
+            configs.append(run_extra_config(torch, ctx, name, gamma, args.gamma, local_rank))
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        avg_launch_s = (sum(per_launch_ms) / len(per_launch_ms)) / 1e3
+        avg_step_s = (sum(per_step_ms) / len(per_step_ms)) / 1e3
         launches_per_step = max(1, launches // max(1, args.steps))
-        ach = algorithmic_bytes(kind, w, h, frames) / avg_launch_s / 1e9
         cpu = cpu_baseline(gamma, w, h)[0] if world == 1 else None
         line = {
             "metric": "Gpix/s BT.709 4:2:0->sRGB BGRA8", "value": all_units / secs / 1e9, "unit": "Gpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": secs / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 math, u8 I/O",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {frames} x {w}x{h} NV12 video-range frames per GPU -> sRGB BGRA8 "
-                                   f"({kind}), gamma={args.gamma if kind != 'alpha' else 'srgb'}",
-                       "frames_per_gpu": frames, "l2": "inputs+outputs per step >> 126 MB L2; no flush needed",
-                       "fps": all_units / (w * h) / secs, "parallelism": f"frame-sharded x{world}, no collective"},
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                         "traffic": ncu_traffic(kind, float(frames) * w * h / launches_per_step), "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algorithmic_bytes(kind, w, h, frames) / launches_per_step,
-                         "avg_launch_ms": avg_launch_s * 1e3, "kernels_per_step": launches_per_step},
+            "config": config_of(args, frames, world, fps=all_units / (w * h) / secs),
+            "roofline": roofline_of(kind, w, h, frames, avg_step_s, launches_per_step),
             "cpu_baseline": cpu,
             "e2e": e2e if e2e else {"value": None, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                                     "note": "e2e is measured on the decode workloads"},
             "gpu_launches": launches,
             "clocks": clocks,
         }
+        if configs is not None:
+            line["configs"] = configs
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-def run_e2e(args, device, w, h, frames, gamma):
-    """Per-frame calls of the reference-facing host API with pinned host buffers."""
+def run_e2e(args, ctx, device, w, h, frames, gamma):
+    """Per-frame calls of the reference-facing host API with pinned host buffers, on the headline's gamma; the
+    read-back of the last pass is compared with the device-resident kernel's output for the same frames."""
     import numpy as np
     from metalbt709decoder_b200 import renderer as R
     import torch
-    tf = {0: R.kMBDTransferFunction_ITU_R_709_2, 1: R.kMBDTransferFunction_sRGB, 2: R.kMBDTransferFunction_Linear}
-    mg = gamma if gamma in (0, 1, 2) else 0  # the ObjC-facing decoder exposes the Metal gammas (Apple default)
+    tf = {0: R.kMBDTransferFunction_ITU_R_709_2, 1: R.kMBDTransferFunction_sRGB, 2: R.kMBDTransferFunction_Linear,
+          3: R.kMBDTransferFunction_ITU_R_709_2}
+    mg = {0: R.MetalBT709GammaApple, 1: R.MetalBT709GammaSRGB, 2: R.MetalBT709GammaLinear, 3: R.MetalBT709GammaBT709Spec}[gamma]
     mrc = R.MetalRenderContext(device)
     assert mrc.setupMetal()
     dec = R.MetalBT709Decoder()
@@ -364,7 +474,7 @@ def run_e2e(args, device, w, h, frames, gamma):
         pb = R.BGRAToBT709Converter.createCoreVideoYCbCrBuffer(w, h)
         pb.y[:] = rng.integers(16, 236, (h, w), dtype=np.uint8)
         pb.cbcr[:] = rng.integers(16, 241, (h // 2, w), dtype=np.uint8)
-        pb.setAttachments(R.kMBDYCbCrMatrix_ITU_R_709_2, tf[mg])
+        pb.setAttachments(R.kMBDYCbCrMatrix_ITU_R_709_2, tf[gamma])
         bufs.append(pb)
         texs.append(mrc.makeBGRATexture(w, h))
     n = min(frames, 200)
@@ -383,8 +493,18 @@ def run_e2e(args, device, w, h, frames, gamma):
         one_pass()
     torch.cuda.synchronize()
     secs = time.perf_counter() - t0
+    # the host path must have produced what the (parity-tested) device-resident kernel produces for the same frames
+    verified = True
+    for i in (0, ring - 1):
+        ty = torch.from_numpy(np.ascontiguousarray(bufs[i].y)).cuda()[None]
+        tc = torch.from_numpy(np.ascontiguousarray(bufs[i].cbcr)).cuda()[None]
+        out = torch.empty((1, h, w, 4), dtype=torch.uint8, device="cuda")
+        ctx.decode_nv12(gamma, ty, tc, out, wait=True)
+        verified = verified and bool(np.array_equal(out[0].cpu().numpy(), texs[i].pixels))
+    if not verified:
+        raise SystemExit("bench.py: e2e output differs from the device-resident kernel's output")
     out = {"_secs": secs, "_units": float(n) * w * h * steps, "h2d": int(n * w * h * 1.5), "d2h": n * w * h * 4,
-           "frames": n, "steps": steps}
+           "frames": n, "steps": steps, "gamma": args.gamma, "verified": verified}
     for b in bufs:
         b.release()
     for t in texs:
@@ -404,6 +524,7 @@ def main():
     ap.add_argument("--gamma", default="bt709", choices=sorted(GAMMAS))
     ap.add_argument("--frames", type=int, default=0, help="override frames per GPU")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the `configs` array (the other BASELINE configurations)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -53,7 +53,11 @@ typedef enum {
   BT709_GAMMA_APPLE = 0,  /* Apple 1.961 curve   AAPLShaders.metal:336-357, BT709.h:821-908 */
   BT709_GAMMA_SRGB = 1,   /* sRGB curve          AAPLShaders.metal:361-382, BT709.h:948-1003 */
   BT709_GAMMA_LINEAR = 2, /* no curve            AAPLShaders.metal:387-407, BT709.h:517-556 */
-  BT709_GAMMA_BT709 = 3   /* BT.709 spec curve   BT709.h:668-738 (decode only) */
+  BT709_GAMMA_BT709 = 3,  /* BT.709 spec curve   BT709.h:668-738 (decode and the packed 4:4:4 pair) */
+  /* packed 4:4:4 entries only: LINEAR-light RGB bytes <-> BT.709 with the spec curve, the reference's
+   * "previous API" BT709_convertRGBToYCbCr / BT709_convertYCbCrToRGB with applyGammaMap = 1
+   * (BT709.h:320-345, 560-607; EmptyiOSTests/CoreImageMetalFilterTests.m:159-360) */
+  BT709_GAMMA_BT709_LINEAR_RGB = 4
 } bt709_gamma;
 
 typedef enum {
@@ -152,6 +156,19 @@ BT709_API int bt709_convert_packed444(const bt709_ctx *ctx, const uint32_t *bgra
                                       int w, int h, void *stream, int wait);
 BT709_API int bt709_unconvert_packed444(const bt709_ctx *ctx, const uint32_t *ycbcr_in, uint32_t *bgra_out,
                                         int w, int h, void *stream, int wait);
+/* The same two kernels with the curve as an argument: the three per-pixel 4:4:4 encoder/decoder pairs of the
+ * reference's CPU path, which its exhaustive 2^24-colour round-trip tests exercise
+ * (EmptyiOSTests/CoreImageMetalFilterTests.m:420-537, 557-674, 696-813):
+ *   BT709_GAMMA_BT709  BT709_from_sRGB_convertRGBToYCbCr / BT709_to_sRGB_convertYCbCrToRGB      (BT709.h:610-738)
+ *   BT709_GAMMA_APPLE  Apple196_from_sRGB_convertRGBToYCbCr / Apple196_to_sRGB_convertYCbCrToRGB (BT709.h:743-908)
+ *   BT709_GAMMA_SRGB   sRGB_from_sRGB_convertRGBToYCbCr / sRGB_to_sRGB_convertYCbCrToRGB         (BT709.h:914-1003)
+ *   BT709_GAMMA_BT709_LINEAR_RGB  BT709_convertRGBToYCbCr / BT709_convertYCbCrToRGB, applyGammaMap = 1
+ *                      (with applyGammaMap = 0 that pair is the BT709_GAMMA_SRGB one: byteNorm, matrix, round)
+ * BT709_GAMMA_LINEAR has no such pair in the reference: BT709_E_GAMMA. */
+BT709_API int bt709_convert_packed444_gamma(const bt709_ctx *ctx, bt709_gamma gamma, const uint32_t *bgra_in,
+                                            uint32_t *ycbcr_out, int w, int h, void *stream, int wait);
+BT709_API int bt709_unconvert_packed444_gamma(const bt709_ctx *ctx, bt709_gamma gamma, const uint32_t *ycbcr_in,
+                                              uint32_t *bgra_out, int w, int h, void *stream, int wait);
 /* +[BGRAToBT709Converter copyBT709ToCoreVideo:cvPixelBuffer:] (BGRAToBT709Converter.m:1042-1099):
  * packed words -> NV12 planes; chroma is taken from the even column of every row, so the
  * odd row's value is the one that survives. */

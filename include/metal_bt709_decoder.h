@@ -38,7 +38,11 @@ extern "C" {
 typedef enum {
   MetalBT709GammaApple = 0, /* default */
   MetalBT709GammaSRGB = 1,
-  MetalBT709GammaLinear = 2
+  MetalBT709GammaLinear = 2,
+  /* Extension (not in the reference's enum): the BT.709 SPEC curve.  The reference's Metal kernels never apply it
+   * (AAPLShaders.metal:94-107 is defined, its caller :144-152 is commented out); its CPU path does
+   * (BT709_to_sRGB_convertYCbCrToRGB, BT709.h:668-738).  Checked against the same transfer tag as the Apple curve. */
+  MetalBT709GammaBT709Spec = 3
 } MetalBT709Gamma;
 
 /* BT709.h:20-25 (note the different numbering) */

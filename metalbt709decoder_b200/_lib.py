@@ -73,6 +73,8 @@ PROTOTYPES = {
     "bt709_encode_bgra_to_nv12": (c_int, [c_void_p, c_int, c_int, PP, PP, PP, c_int, c_int, c_int, c_void_p, c_int]),
     "bt709_convert_packed444": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),
     "bt709_unconvert_packed444": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),
+    "bt709_convert_packed444_gamma": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),
+    "bt709_unconvert_packed444_gamma": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),
     "bt709_copy_packed444_to_nv12": (c_int, [c_void_p, c_void_p, PP, PP, c_int, c_int, c_void_p, c_int]),
     # include/y4m_b200.h
     "y4m_open_file": (c_void_p, [ctypes.c_char_p]),

@@ -27,9 +27,9 @@ struct bt709_ctx {
   mutable std::atomic<unsigned long long> launches{0};
   void *dev_blob = nullptr;  // one allocation holding every table below
   // decode: matrix output -> sRGB byte, per bt709_gamma
-  const uint32_t *dec_lut[4] = {};
-  float dec_clamp[4] = {};
-  int dec_cells[4] = {};
+  const uint32_t *dec_lut[5] = {};  // [4] = kBt709LinearRgb, packed 4:4:4 entries only
+  float dec_clamp[5] = {};
+  int dec_cells[5] = {};
   // log-cell form of the Linear-mode step function (conflict-free when replicated per lane)
   const uint32_t *dec_log_lut = nullptr;
   float dec_log_clamp = 0.f;
@@ -41,7 +41,9 @@ struct bt709_ctx {
   int fl_cells[3] = {};
   const float *lin256[3] = {};       // BT709_tolinearNorm per input gamma
   const float *compn256[3][3] = {};  // [gin][gout] unorm8(from_linear(to_linear(b)))
-  const float *enc444_apple = nullptr;
+  // per-pixel 4:4:4 encoders: sRGB byte -> non-linear value fed to the matrix, per bt709_gamma
+  // (BT709.h:610-664 BT.709 curve, :743-817 Apple curve, :914-944 sRGB = byteNorm; Linear has no such encoder)
+  const float *enc444[5] = {};
   MatrixConsts m;
 };
 
@@ -124,8 +126,8 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
 
   // ---- build every table on the host, once
   BlobBuilder blob;
-  size_t off_dec[4], off_fl[3], off_lin[3], off_comp[3][3], off_e444, off_log = 0;
-  for (int g = 0; g < 4; g++) {
+  size_t off_dec[5], off_fl[3], off_lin[3], off_comp[3][3], off_e444[5] = {}, off_log = 0;
+  for (int g = 0; g < 5; g++) {
     StepFn fn;
     CellLut lut;
     if (!build_step_fn(decode_code, g, &fn)) { delete ctx; return BT709_E_GAMMA; }
@@ -164,10 +166,14 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
       for (int b = 0; b < 256; b++) t[b] = from_linear_code(go, to_linear(gi, b)) * (1.0f / 255.0f);
       off_comp[gi][go] = blob.add(t, 256);
     }
-  {
-    float t[256];  // Apple196_from_sRGB_convertRGBToYCbCr front half, BT709.h:771-808
-    for (int b = 0; b < 256; b++) t[b] = apple_oetf(srgb_eotf(b * (1.0f / 255.0f)));
-    off_e444 = blob.add(t, 256);
+  for (int g = 0; g < 5; g++) {
+    if (g == kLinear) continue;
+    float t[256];  // front half of the per-pixel encoders: byteNorm, sRGB -> linear, linear -> gamma g
+    for (int b = 0; b < 256; b++) {
+      const float n = b * (1.0f / 255.0f);
+      t[b] = g == kSrgb ? n : g == kApple ? apple_oetf(srgb_eotf(n)) : g == kBt709 ? bt709_oetf(srgb_eotf(n)) : bt709_oetf(n);
+    }
+    off_e444[g] = blob.add(t, 256);
   }
 
   if ((e = cudaMalloc(&ctx->dev_blob, blob.words.size() * 4)) != cudaSuccess) { delete ctx; return BT709_E_CUDA; }
@@ -177,14 +183,15 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
     return BT709_E_CUDA;
   }
   const uint32_t *base = (const uint32_t *) ctx->dev_blob;
-  for (int g = 0; g < 4; g++) ctx->dec_lut[g] = base + off_dec[g];
+  for (int g = 0; g < 5; g++) ctx->dec_lut[g] = base + off_dec[g];
   if (ctx->dec_log_cells) ctx->dec_log_lut = base + off_log;
   for (int g = 0; g < 3; g++) {
     ctx->fl_lut[g] = base + off_fl[g];
     ctx->lin256[g] = (const float *) (base + off_lin[g]);
     for (int go = 0; go < 3; go++) ctx->compn256[g][go] = (const float *) (base + off_comp[g][go]);
   }
-  ctx->enc444_apple = (const float *) (base + off_e444);
+  for (int g = 0; g < 5; g++)
+    if (g != kLinear) ctx->enc444[g] = (const float *) (base + off_e444[g]);
   int ke = kernels_init();
   if (ke) {
     cudaFree(ctx->dev_blob);
@@ -324,29 +331,41 @@ int bt709_encode_bgra_to_nv12(const bt709_ctx *ctx, bt709_gamma gin, bt709_gamma
   return finish(ctx, l0, launch_encode(a, ctx->sm_count, stream), stream, wait);
 }
 
-int bt709_convert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t *out, int w, int h, void *stream,
-                            int wait) {
+int bt709_convert_packed444_gamma(const bt709_ctx *ctx, bt709_gamma gamma, const uint32_t *in, uint32_t *out, int w, int h,
+                                  void *stream, int wait) {
   if (!ctx || !in || !out) return BT709_E_NULL;
   if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) return BT709_E_DIMS;  // BGRAToBT709Converter.m:41-46
+  if ((int) gamma < 0 || (int) gamma > 4 || !ctx->enc444[gamma]) return BT709_E_GAMMA;
   DeviceGuard guard(ctx->device);
   if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
   Packed444Args a{};
-  a.in = in; a.out = out; a.n = (long long) w * h; a.enc256 = ctx->enc444_apple; a.m = ctx->m;
+  a.in = in; a.out = out; a.n = (long long) w * h; a.enc256 = ctx->enc444[gamma]; a.m = ctx->m;
   const unsigned long long l0 = launches_begin();
   return finish(ctx, l0, launch_convert444(a, stream), stream, wait);
 }
 
-int bt709_unconvert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t *out, int w, int h, void *stream,
-                              int wait) {
+int bt709_unconvert_packed444_gamma(const bt709_ctx *ctx, bt709_gamma gamma, const uint32_t *in, uint32_t *out, int w,
+                                    int h, void *stream, int wait) {
   if (!ctx || !in || !out) return BT709_E_NULL;
   if (w <= 0 || h <= 0 || (w & 1) || (h & 1)) return BT709_E_DIMS;  // BGRAToBT709Converter.m:69-74
+  if ((int) gamma < 0 || (int) gamma > 4 || (int) gamma == (int) kLinear) return BT709_E_GAMMA;
   DeviceGuard guard(ctx->device);
   if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
   Packed444Args a{};
   a.in = in; a.out = out; a.n = (long long) w * h; a.m = ctx->m;
-  a.lut = ctx->dec_lut[kApple]; a.clamp_lo = ctx->dec_clamp[kApple]; a.cells_log2 = ctx->dec_cells[kApple];
+  a.lut = ctx->dec_lut[gamma]; a.clamp_lo = ctx->dec_clamp[gamma]; a.cells_log2 = ctx->dec_cells[gamma];
   const unsigned long long l0 = launches_begin();
   return finish(ctx, l0, launch_unconvert444(a, stream), stream, wait);
+}
+
+int bt709_convert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t *out, int w, int h, void *stream,
+                            int wait) {
+  return bt709_convert_packed444_gamma(ctx, BT709_GAMMA_APPLE, in, out, w, h, stream, wait);
+}
+
+int bt709_unconvert_packed444(const bt709_ctx *ctx, const uint32_t *in, uint32_t *out, int w, int h, void *stream,
+                              int wait) {
+  return bt709_unconvert_packed444_gamma(ctx, BT709_GAMMA_APPLE, in, out, w, h, stream, wait);
 }
 
 int bt709_copy_packed444_to_nv12(const bt709_ctx *ctx, const uint32_t *in, const bt709_plane *y,

@@ -106,6 +106,7 @@ bt709_gamma to_abi_gamma(MetalBT709Gamma g) {
   switch (g) {
     case MetalBT709GammaSRGB: return BT709_GAMMA_SRGB;
     case MetalBT709GammaLinear: return BT709_GAMMA_LINEAR;
+    case MetalBT709GammaBT709Spec: return BT709_GAMMA_BT709;
     default: return BT709_GAMMA_APPLE;
   }
 }
@@ -157,7 +158,7 @@ bool decode_args_ok(const MetalBT709Decoder *d, const MBDPixelBuffer *pb, const 
   }
   if (pb->yCbCrMatrix != kMBDYCbCrMatrix_ITU_R_709_2) return false;        // :311-318
   const int tf = pb->transferFunction;                                     // :320-353
-  if (gamma == MetalBT709GammaApple && tf != kMBDTransferFunction_ITU_R_709_2) return false;
+  if ((gamma == MetalBT709GammaApple || gamma == MetalBT709GammaBT709Spec) && tf != kMBDTransferFunction_ITU_R_709_2) return false;
   if (gamma == MetalBT709GammaSRGB && tf != kMBDTransferFunction_sRGB) return false;
   if (gamma == MetalBT709GammaLinear && tf != kMBDTransferFunction_Linear) return false;
   if (alpha && alpha->transferFunction != kMBDTransferFunction_Linear) return false;  // :357-368
@@ -288,7 +289,7 @@ int MetalBT709Decoder_setupMetal(MetalBT709Decoder *d) {
     d->owns_mrc = true;
   }
   if (!d->mrc || !MetalRenderContext_setupMetal(d->mrc)) return 0;
-  if ((unsigned) d->gamma > (unsigned) MetalBT709GammaLinear) return 0;  // :125,177 assert(0)
+  if ((unsigned) d->gamma > (unsigned) MetalBT709GammaBT709Spec) return 0;  // :125,177 assert(0)
   // :108 the compute pipeline does not support an alpha channel
   if (d->useComputeRenderer && d->hasAlphaChannel) return 0;
   // :165-169 an alpha channel forces the sRGB gamma

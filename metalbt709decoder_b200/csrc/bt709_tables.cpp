@@ -42,6 +42,14 @@ float bt709_eotf(float v) {
   return (float) std::pow((double) s, (double) g);
 }
 
+// BT709.h:90-103 (the whole right-hand side is a double expression rounded to float once)
+float bt709_oetf(float v) {
+  if (v < 0.018f) return v * 4.5f;
+  const float a = 0.099f;
+  const float g = 0.45f;
+  return (float) ((double) (1.0f + a) * std::pow((double) v, (double) g) - (double) a);
+}
+
 static const float kAppleGamma = 1.960938f;
 
 float apple_eotf(float v) {
@@ -62,6 +70,7 @@ int decode_code(int gamma, float x) {
     case kApple: return quant255(srgb_oetf(apple_eotf(x)));
     case kBt709: return quant255(srgb_oetf(bt709_eotf(x)));
     case kLinear: return quant255(srgb_oetf(x));
+    case kBt709LinearRgb: return quant255(bt709_eotf(x));  // BT709_convertYCbCrToRGB(applyGammaMap = 1): linear RGB out
     default: return quant255(x);
   }
 }

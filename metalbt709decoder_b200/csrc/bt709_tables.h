@@ -17,12 +17,15 @@
 
 namespace bt709 {
 
-enum Gamma { kApple = 0, kSrgb = 1, kLinear = 2, kBt709 = 3 };
+// kBt709LinearRgb: the reference's "previous API" pair BT709_convertRGBToYCbCr / BT709_convertYCbCrToRGB with
+// applyGammaMap = 1 (linear-light RGB bytes <-> BT.709, BT709.h:320-345, 560-607); packed 4:4:4 entries only
+enum Gamma { kApple = 0, kSrgb = 1, kLinear = 2, kBt709 = 3, kBt709LinearRgb = 4 };
 
 // ---- scalar curve math with the reference's float32/double semantics ----------------
 float srgb_eotf(float v);   // sRGB.h:43-57
 float srgb_oetf(float v);   // sRGB.h:62-74
 float bt709_eotf(float v);  // BT709.h:68-81
+float bt709_oetf(float v);  // BT709.h:90-103
 float apple_eotf(float v);  // BT709.h:125-137
 float apple_oetf(float v);  // BT709.h:139-151
 int quant255(float v);      // BT709.h:711-713

@@ -104,7 +104,7 @@ class BT709Context:
     def decode_rescale_nv12(self, gamma, y, cbcr, scratch, out, alpha_y=None, w=None, h=None, stream=None, wait=False):
         F, H = y.shape[0], y.shape[1]
         h = h if h is not None else H
-        w = w if w is not None else (scratch.shape[2] if scratch is not None else out.shape[2])
+        w = w if w is not None else (scratch.shape[2] if scratch is not None else y.shape[2])
         oh, ow = out.shape[1], out.shape[2]
         py, pc, po = plane_of(y), plane_of(cbcr), plane_of(out)
         ps = plane_of(scratch) if scratch is not None else None
@@ -125,19 +125,20 @@ class BT709Context:
         if rc != OK:
             raise BT709Error(rc, "bt709_encode_bgra_to_nv12")
 
-    def convert_packed444(self, bgra_words, out_words, stream=None, wait=False):
+    def convert_packed444(self, bgra_words, out_words, stream=None, wait=False, gamma=GAMMA_APPLE):
+        """(h,w) int32 BGRA words -> Cr<<16 | Cb<<8 | Y; gamma picks the per-pixel encoder (BT709.h:610-944)."""
         h, w = bgra_words.shape
-        rc = self._L.bt709_convert_packed444(self._h, bgra_words.data_ptr(), out_words.data_ptr(), w, h,
-                                             _stream_ptr(stream), int(wait))
+        rc = self._L.bt709_convert_packed444_gamma(self._h, int(gamma), bgra_words.data_ptr(), out_words.data_ptr(), w, h,
+                                                   _stream_ptr(stream), int(wait))
         if rc != OK:
-            raise BT709Error(rc, "bt709_convert_packed444")
+            raise BT709Error(rc, "bt709_convert_packed444_gamma")
 
-    def unconvert_packed444(self, ycbcr_words, out_words, stream=None, wait=False):
+    def unconvert_packed444(self, ycbcr_words, out_words, stream=None, wait=False, gamma=GAMMA_APPLE):
         h, w = ycbcr_words.shape
-        rc = self._L.bt709_unconvert_packed444(self._h, ycbcr_words.data_ptr(), out_words.data_ptr(), w, h,
-                                               _stream_ptr(stream), int(wait))
+        rc = self._L.bt709_unconvert_packed444_gamma(self._h, int(gamma), ycbcr_words.data_ptr(), out_words.data_ptr(),
+                                                     w, h, _stream_ptr(stream), int(wait))
         if rc != OK:
-            raise BT709Error(rc, "bt709_unconvert_packed444")
+            raise BT709Error(rc, "bt709_unconvert_packed444_gamma")
 
     def copy_packed444_to_nv12(self, ycbcr_words, y, cbcr, stream=None, wait=False):
         h, w = ycbcr_words.shape

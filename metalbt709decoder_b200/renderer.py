@@ -14,6 +14,7 @@ import numpy as np
 from . import _lib
 
 MetalBT709GammaApple, MetalBT709GammaSRGB, MetalBT709GammaLinear = 0, 1, 2
+MetalBT709GammaBT709Spec = 3  # extension: the BT.709 spec curve of the reference's CPU path (BT709.h:668-738)
 BT709GammaSrgb, BT709GammaApple, BT709GammaLinear = 1, 2, 3
 BGRAToBT709ConverterSoftware, BGRAToBT709ConverterVImage, BGRAToBT709ConverterMetal = 0, 1, 2
 kMBDYCbCrMatrix_Untagged, kMBDYCbCrMatrix_ITU_R_709_2, kMBDYCbCrMatrix_ITU_R_601_4 = 0, 1, 2

@@ -1,0 +1,343 @@
+"""Round-2 parity tests (-m gpu), all through the C ABI:
+  * the GPU against oracle/_ref (the reference's own BT709.h compiled where it lies) DIRECTLY, so the parity chain
+    GPU == reference closes inside the driver's -m gpu run and not only through the restatement;
+  * the CoreImageMetalFilterTests.m goldens (five 4:2:0 averaging vectors, nine BT.709-curve pixel tests) replayed on
+    the device, and the three exhaustive 2^24-colour round-trip histograms reproduced on the device;
+  * the geometries of the linear-tile-stream decode kernel (k_decode_lin) and its few-replica variant;
+  * the encode launcher's 32-bit offset split, and slot reuse of the host layer across caller streams.
+"""
+import ctypes
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from _oracle import GAMMA_APPLE, GAMMA_BT709, GAMMA_LINEAR, GAMMA_SRGB, Oracle, bgra_random, frame_lattice, frame_random, ref_oracle
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+VEC = json.load(open(os.path.join(HERE, "golden", "reference_vectors.json")))
+ORA = Oracle()
+GAMMA_BT709_LINEAR_RGB = 4
+
+
+def _ref():
+    r = ref_oracle()
+    if r is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return r
+
+
+# ------------------------------------------------------------------ GPU == reference, directly
+@pytest.mark.parametrize("gamma", [0, 1, 2, 3])
+def test_lattice_decode_equals_the_reference_headers(gamma):
+    """all 2^24 (Y,Cb,Cr) inputs: bt709_decode_nv12 against BT709.h/sRGB.h compiled unmodified (oracle/_ref)"""
+    from _gpu import decode
+    ref = _ref()
+    y, c = frame_lattice()
+    got = decode(gamma, y, c)
+    want = ref.decode_nv12(gamma, y, c)
+    assert np.array_equal(got[..., :3], want[..., :3]), f"gamma {gamma}: {(got[..., :3] != want[..., :3]).sum()} mismatches"
+    assert (got[..., 3] == 255).all()
+
+
+@pytest.mark.parametrize("gin,gout", [(1, 0), (1, 1), (2, 2), (0, 0), (1, 2), (0, 1)])
+def test_encode_equals_the_reference_headers(gin, gout):
+    """bt709_encode_bgra_to_nv12 against BT709_average_pixel_values of the reference (oracle/_ref), six gamma pairs"""
+    from _gpu import ctx, dev
+    ref = _ref()
+    w, h = 256, 64
+    src = bgra_random(w, h, seed=900 + gin * 3 + gout)
+    ty = torch.zeros((1, h, w), dtype=torch.uint8, device="cuda")
+    tc = torch.zeros((1, h // 2, w), dtype=torch.uint8, device="cuda")
+    ctx().encode_bgra_to_nv12(gin, gout, dev(src)[None], ty, tc, wait=True)
+    wy, wc = ref.encode_bgra_nv12(gin, gout, src)
+    assert np.array_equal(ty[0].cpu().numpy(), wy) and np.array_equal(tc[0].cpu().numpy(), wc)
+
+
+# ------------------------------------------------------------------ CoreImageMetalFilterTests.m on the device
+CI = {t["name"]: t for t in VEC["files"]["CoreImageMetalFilterTests.m"]}
+REF_GAMMA = {"BT709GammaSrgb": GAMMA_SRGB, "BT709GammaApple": GAMMA_APPLE, "BT709GammaLinear": GAMMA_LINEAR}
+
+
+def _chk(t):
+    return {c["var"]: c["expected"] for c in t["checks"]}
+
+
+def _convert444(gamma, r, g, b):
+    """one colour as a 2x2 frame through bt709_convert_packed444_gamma -> (Y, Cb, Cr)"""
+    from _gpu import ctx
+    words = torch.full((2, 2), (0xFF << 24) | (r << 16) | (g << 8) | b, dtype=torch.int64).to(torch.int32).cuda()
+    out = torch.zeros((2, 2), dtype=torch.int32, device="cuda")
+    ctx().convert_packed444(words, out, wait=True, gamma=gamma)
+    v = out.cpu().numpy().astype(np.uint32)
+    assert (v == v[0, 0]).all()
+    p = int(v[0, 0])
+    return p & 255, (p >> 8) & 255, (p >> 16) & 255
+
+
+def _unconvert444(gamma, y, cb, cr):
+    from _gpu import ctx
+    words = torch.full((2, 2), (cr << 16) | (cb << 8) | y, dtype=torch.int32, device="cuda")
+    out = torch.zeros((2, 2), dtype=torch.int32, device="cuda")
+    ctx().unconvert_packed444(words, out, wait=True, gamma=gamma)
+    p = int(out.cpu().numpy().astype(np.uint32)[1, 1])
+    return (p >> 16) & 255, (p >> 8) & 255, p & 255
+
+
+def _decode_2x2(gamma, y, cb, cr):
+    from _gpu import decode
+    got = decode(gamma, np.full((2, 2), y, np.uint8), np.array([[cb, cr]], np.uint8))
+    assert (got == got[0, 0]).all()
+    return int(got[0, 0, 2]), int(got[0, 0, 1]), int(got[0, 0, 0])
+
+
+@pytest.mark.parametrize("name", [n for n in CI if n.startswith("testConvertsLinearRGBToBT709_") and "srgb" not in n])
+def test_linear_rgb_to_bt709_goldens_on_the_device(name):
+    """CoreImageMetalFilterTests.m:94-360: BT709_convertRGBToYCbCr / BT709_convertYCbCrToRGB with and without the
+    BT.709 curve.  Without it the pair is byteNorm -> matrix -> round, i.e. the sRGB-tagged pair."""
+    t = CI[name]
+    c, i = _chk(t), t["inputs"]
+    g = GAMMA_BT709_LINEAR_RGB if i["applyGammaMap"] else GAMMA_SRGB
+    assert _convert444(g, i["Rin"], i["Gin"], i["Bin"]) == (c["Y"], c["Cb"], c["Cr"])
+    assert _unconvert444(g, c["Y"], c["Cb"], c["Cr"]) == (c["R"], c["G"], c["B"])
+
+
+@pytest.mark.parametrize("name", ["testConvertsLinearRGBToBT709_42PercentBlue_srgb",
+                                  "testConvertsSRGBToYCbCr_ResampleUpperNW", "testConvertsSRGBToYCbCr_ResampleUpperNE",
+                                  "testConvertsSRGBToYCbCr_ResampleUpperSW", "testConvertsSRGBToYCbCr_ResampleUpperSE"])
+def test_bt709_spec_curve_goldens_on_the_device(name):
+    """CoreImageMetalFilterTests.m:362-416, 851-1073: BT709_from_sRGB_convertRGBToYCbCr on the device (E1 + E4), then
+    BT709_to_sRGB_convertYCbCrToRGB both through the packed harness kernel and through bt709_decode_nv12"""
+    t = CI[name]
+    c, i = _chk(t), t["inputs"]
+    assert _convert444(GAMMA_BT709, i["Rin"], i["Gin"], i["Bin"]) == (c["Y"], c["Cb"], c["Cr"])
+    assert _unconvert444(GAMMA_BT709, c["Y"], c["Cb"], c["Cr"]) == (c["R"], c["G"], c["B"])
+    assert _decode_2x2(GAMMA_BT709, c["Y"], c["Cb"], c["Cr"]) == (c["R"], c["G"], c["B"])
+
+
+@pytest.mark.parametrize("name", [n for n in CI if n.startswith("testConvertsSRGBToYCbCr_AverageOf4")])
+def test_average_of_4_goldens_on_the_device(name):
+    """CoreImageMetalFilterTests.m:1683-2094: BT709_average_pixel_values vectors as one 2x2 frame through
+    bt709_encode_bgra_to_nv12"""
+    from _gpu import ctx
+    t = CI[name]
+    c, i = _chk(t), t["inputs"]
+    gin, gout = REF_GAMMA[t["gammas"]["inputGamma"]], REF_GAMMA[t["gammas"]["outputGamma"]]
+    px = np.zeros((2, 2, 4), np.uint8)
+    for k, (row, col) in enumerate([(0, 0), (0, 1), (1, 0), (1, 1)], start=1):  # NW, NE, SW, SE
+        px[row, col] = (i[f"B{k}"], i[f"G{k}"], i[f"R{k}"], 255)
+    ty = torch.zeros((1, 2, 2), dtype=torch.uint8, device="cuda")
+    tc = torch.zeros((1, 1, 2), dtype=torch.uint8, device="cuda")
+    ctx().encode_bgra_to_nv12(gin, gout, torch.from_numpy(px).cuda()[None], ty, tc, wait=True)
+    assert ty[0].cpu().numpy().reshape(-1).tolist() == [c["Y1"], c["Y2"], c["Y3"], c["Y4"]]
+    assert tc[0, 0].cpu().numpy().tolist() == [c["Cb"], c["Cr"]]
+
+
+@pytest.mark.parametrize("key", ["bt709", "apple", "srgb"])
+def test_2_24_roundtrip_histograms_on_the_device(key):
+    """CoreImageMetalFilterTests.m:420-537, 557-674, 696-813: every sRGB colour through the per-pixel encoder and
+    decoder of one curve, bucketed by the largest channel difference; every bucket must match the reference's
+    recorded counts (all three encoders and decoders run on the GPU)"""
+    from _gpu import ctx
+    hspec = VEC["histograms"][key]
+    g = hspec["gamma"]
+    n = torch.arange(1 << 24, dtype=torch.int32, device="cuda").view(4096, 4096)
+    ycc = torch.empty_like(n)
+    back = torch.empty_like(n)
+    ctx().convert_packed444(n, ycc, gamma=g)
+    ctx().unconvert_packed444(ycc, back, gamma=g, wait=True)
+    dmax = torch.zeros_like(n)
+    for sh in (0, 8, 16):
+        d = (((n >> sh) & 255) - ((back >> sh) & 255)).abs()
+        dmax = torch.maximum(dmax, d)
+    hist = torch.bincount(dmax.view(-1), minlength=11).cpu().tolist()
+    assert hist[0] == hspec["exact"]
+    assert hist[:len(hspec["buckets"])] == hspec["buckets"]
+    assert sum(hist) == 1 << 24 and sum(hist[len(hspec["buckets"]):]) == 0
+
+
+@pytest.mark.parametrize("gamma", [GAMMA_APPLE, GAMMA_SRGB, GAMMA_BT709, GAMMA_BT709_LINEAR_RGB])
+def test_packed444_gamma_variants_match_the_oracle(gamma):
+    from _gpu import ctx
+    rng = np.random.default_rng(1234 + gamma)
+    h, w = 32, 48
+    words = rng.integers(0, 1 << 24, (h, w), dtype=np.uint32)
+    tin = torch.from_numpy(words.astype(np.int32)).cuda()
+    tout = torch.zeros_like(tin)
+    ctx().convert_packed444(tin, tout, wait=True, gamma=gamma)
+    got = tout.cpu().numpy().astype(np.uint32)
+    back = torch.zeros_like(tin)
+    ctx().unconvert_packed444(tout, back, wait=True, gamma=gamma)
+    gotb = back.cpu().numpy().astype(np.uint32)
+    for (r_, c_) in [(int(a), int(b)) for a, b in zip(rng.integers(0, h, 300), rng.integers(0, w, 300))]:
+        p = int(words[r_, c_])
+        R, G, B = (p >> 16) & 255, (p >> 8) & 255, p & 255
+        if gamma == GAMMA_BT709_LINEAR_RGB:
+            Y, Cb, Cr = ORA.linear_rgb_to_ycbcr(R, G, B, 1)
+            rr = ORA.ycbcr_to_linear_rgb(Y, Cb, Cr, 1)
+        else:
+            Y, Cb, Cr = ORA.encode444_pixel(gamma, R, G, B)
+            rr = ORA.decode_pixel(gamma, Y, Cb, Cr)
+        assert int(got[r_, c_]) == (Cr << 16) | (Cb << 8) | Y
+        q = int(gotb[r_, c_])
+        assert ((q >> 16) & 255, (q >> 8) & 255, q & 255) == rr and (q >> 24) == 0
+
+
+def test_packed444_gamma_errors():
+    from _gpu import ctx
+    from metalbt709decoder_b200 import BT709Error
+    a = torch.zeros((2, 2), dtype=torch.int32, device="cuda")
+    for g in (2, 5, -1):
+        with pytest.raises(BT709Error) as e:
+            ctx().convert_packed444(a, a.clone(), gamma=g)
+        assert e.value.status == -4
+        with pytest.raises(BT709Error) as e:
+            ctx().unconvert_packed444(a, a.clone(), gamma=g)
+        assert e.value.status == -4
+
+
+# ------------------------------------------------------------------ k_decode_lin geometries
+LIN_CASES = [
+    # w, h, frames, gamma, alpha
+    (1920, 1080, 3, 3, False),   # 15 tiles per row, replicated LUT (24300 tiles)
+    (1920, 1080, 3, 2, False),   # Linear mode: log-cell LUT, compact ring slices, 30 warps per CTA
+    (2048, 1536, 2, 1, True),    # alpha stream, 16 tiles per row
+    (1920, 1080, 1, 0, False),   # one frame per call: the few-replica variant
+    (1920, 2, 1, 3, False),      # a single row pair
+    (128, 2, 1, 1, False),       # a single tile
+    (128, 64, 40, 0, False),     # one tile per row, many frames
+    (4224, 4, 2, 3, False),      # 33 tiles per row (more than the warps of a CTA)
+    (8192, 8, 2, 2, False),      # 64 tiles per row, Linear mode
+    (3840, 6, 5, 1, True),       # UHD width with alpha, small call
+    (640, 360, 9, 3, False),     # 5 tiles per row
+]
+
+
+@pytest.mark.parametrize("w,h,F,gamma,alpha", LIN_CASES)
+def test_linear_tile_stream_kernel(w, h, F, gamma, alpha):
+    from _gpu import ctx, dev
+    frames = [frame_random(w, h, seed=500 + f, full_range=(f % 2 == 1)) for f in range(F)]
+    ty = torch.stack([dev(y) for y, _ in frames])
+    tc = torch.stack([dev(c) for _, c in frames])
+    alphas, ta = None, None
+    if alpha:
+        alphas = [frame_random(w, h, seed=600 + f, full_range=True)[0] for f in range(F)]
+        ta = torch.stack([dev(a) for a in alphas])
+    out = torch.zeros((F, h, w, 4), dtype=torch.uint8, device="cuda")
+    n0 = ctx().launch_count
+    ctx().decode_nv12(gamma, ty, tc, out, alpha_y=ta, wait=True)
+    assert ctx().launch_count == n0 + 1
+    got = out.cpu().numpy()
+    for f in range(F):
+        want = ORA.decode_nv12(gamma, frames[f][0], frames[f][1], alpha_y=alphas[f] if alpha else None)
+        assert np.array_equal(got[f], want), f"{w}x{h} frame {f}: {(got[f] != want).sum()} byte mismatches"
+
+
+@pytest.mark.parametrize("env", [{"BT709_SMALL_STEPS": "0"}, {"BT709_SMALL_STEPS": "1000000"}, {"BT709_NO_LIN2": "1"}])
+def test_decode_lut_replication_variants_in_a_subprocess(env):
+    """BT709_SMALL_STEPS=0: the per-lane replicated LUT even for tiny calls; =1000000: the few-replica LUT even for
+    batches; BT709_NO_LIN2: the round-1 kernels.  Each must stay exact (env is read once per process)."""
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, "tests")
+from _oracle import Oracle, frame_random
+from _gpu import ctx, dev
+ora = Oracle()
+for (w, h, F, g, al) in [(1920, 64, 2, 3, False), (3840, 8, 3, 2, False), (2048, 16, 2, 1, True), (384, 6, 4, 0, False), (4224, 4, 2, 2, False)]:
+    fr = [frame_random(w, h, seed=70 + f) for f in range(F)]
+    ty = torch.stack([dev(y) for y, _ in fr]); tc = torch.stack([dev(c) for _, c in fr])
+    al_np = [frame_random(w, h, seed=80 + f, full_range=True)[0] for f in range(F)] if al else None
+    ta = torch.stack([dev(a) for a in al_np]) if al else None
+    out = torch.zeros((F, h, w, 4), dtype=torch.uint8, device="cuda")
+    ctx().decode_nv12(g, ty, tc, out, alpha_y=ta, wait=True)
+    got = out.cpu().numpy()
+    for f in range(F):
+        assert np.array_equal(got[f], ora.decode_nv12(g, fr[f][0], fr[f][1], alpha_y=al_np[f] if al else None)), (w, h, g, f)
+print("variant ok")
+'''
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, **env), capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout + r.stderr
+
+
+# ------------------------------------------------------------------ encode: offsets beyond 32-bit units
+def test_encode_output_offsets_beyond_32_bits_are_split():
+    """Y / CbCr planes with a padded frame stride: the batch's Y offsets pass 2^32 four-byte units (16 GiB) although
+    the BGRA input is tiny.  The fast encode kernel addresses every plane with 32-bit unit offsets, so the launcher
+    must split the batch; before the fix frames past the wrap were written into the wrong place."""
+    from _gpu import ctx
+    from metalbt709decoder_b200._lib import Plane
+    w, h, F = 256, 8, 5
+    stride_y = (9 << 29) + 4096      # 4.5 GiB between Y frames: frame 4 starts at 18 GiB
+    stride_c = (5 << 30) + 8192      # 5 GiB between CbCr frames
+    free, _ = torch.cuda.mem_get_info()
+    need = (stride_y + stride_c) * (F - 1) + (1 << 30)
+    if free < need:
+        pytest.skip("not enough free device memory")
+    ybuf = torch.empty(stride_y * (F - 1) + w * h, dtype=torch.uint8, device="cuda")
+    cbuf = torch.empty(stride_c * (F - 1) + w * h // 2, dtype=torch.uint8, device="cuda")
+    src = np.stack([bgra_random(w, h, seed=820 + f) for f in range(F)])
+    tsrc = torch.from_numpy(src).cuda()
+    for f in range(F):
+        ybuf[f * stride_y:f * stride_y + w * h] = 0
+        cbuf[f * stride_c:f * stride_c + w * h // 2] = 0
+    C = ctx()
+    pi = Plane(tsrc.data_ptr(), w * 4, w * h * 4)
+    py = Plane(ybuf.data_ptr(), w, stride_y)
+    pc = Plane(cbuf.data_ptr(), w, stride_c)
+    n0 = C.launch_count
+    rc = C._L.bt709_encode_bgra_to_nv12(C.handle, 1, 0, ctypes.byref(pi), ctypes.byref(py), ctypes.byref(pc), w, h, F,
+                                        ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), 1)
+    assert rc == 0
+    assert C.launch_count - n0 >= 2, "the batch must have been split across launches"
+    for f in range(F):
+        wy, wc = ORA.encode_bgra_nv12(1, 0, src[f])
+        gy = ybuf[f * stride_y:f * stride_y + w * h].view(h, w).cpu().numpy()
+        gc = cbuf[f * stride_c:f * stride_c + w * h // 2].view(h // 2, w).cpu().numpy()
+        assert np.array_equal(gy, wy) and np.array_equal(gc, wc), f"frame {f}"
+
+
+# ------------------------------------------------------------------ host layer: slot reuse across streams
+def test_host_layer_mixes_caller_streams_and_internal_streams():
+    """More calls than staging slots on one MetalRenderContext, alternating a caller stream (commandBuffer) and NULL:
+    a slot's reuse must always be ordered after its previous work (it was only ordered when the NEW call
+    brought its own stream)"""
+    from metalbt709decoder_b200 import renderer as R
+    mrc = R.MetalRenderContext(0)
+    assert mrc.setupMetal()
+    dec = R.MetalBT709Decoder()
+    dec.metalRenderContext = mrc
+    dec.gamma = R.MetalBT709GammaSRGB
+    w, h, n = 1920, 1080, 13
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    bufs, texs, wants = [], [], []
+    for i in range(n):
+        y, c = frame_random(w, h, seed=1000 + i)
+        pb = R.BGRAToBT709Converter.createCoreVideoYCbCrBuffer(w, h)
+        pb.y[:] = y
+        pb.cbcr[:] = c
+        pb.setAttachments(R.kMBDYCbCrMatrix_ITU_R_709_2, R.kMBDTransferFunction_sRGB)
+        bufs.append(pb)
+        texs.append(mrc.makeBGRATexture(w, h))
+        wants.append((y, c))
+    for i in range(n):
+        cb = None if i % 3 == 0 else streams[i % 2].cuda_stream
+        assert dec.decodeBT709(bufs[i], None, texs[i], cb, w, h, False)
+    for s in streams:
+        s.synchronize()
+    assert mrc.waitUntilCompleted()
+    for i in (0, 1, 4, 5, 8, 12):
+        got = mrc.getBGRATexturePixels(texs[i]).view(np.uint8).reshape(h, w, 4)
+        assert np.array_equal(got, ORA.decode_nv12(1, *wants[i])), f"call {i}"
+    for b in bufs:
+        b.release()
+    for t in texs:
+        t.release()
+    dec.release()
+    mrc.release()
