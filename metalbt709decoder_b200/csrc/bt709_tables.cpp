@@ -205,6 +205,52 @@ int log_lut_eval(const LogLut &lut, float x) {
   return (int) ((lut.entries[(f2u(xc) >> 16) - lut.first] + f2u(xc)) >> 24);
 }
 
+bool build_biased_log_lut(const StepFn &fn, float bias, BiasedLogLut *out) {
+  if (!(fn.thr[1] > 0.0f) || fn.thr[1] > 1.0f || !(bias > 0.0f)) return false;
+  // clamp: the largest power of two not above the first threshold (code 0 below it either way)
+  int e;
+  std::frexp(fn.thr[1], &e);  // thr[1] = m * 2^e, m in [0.5, 1)
+  const float clamp_lo = std::ldexp(1.0f, e - 1);
+  auto cell_of = [&](float x) { return f2u(x + bias) >> 16; };  // float32 add, round to nearest (no contraction: plain +)
+  const uint32_t first = cell_of(clamp_lo), last = cell_of(1.0f);
+  out->clamp_lo = clamp_lo;
+  out->bias = bias;
+  out->first = first;
+  out->entries.assign(last - first + 1, 0u);
+  const uint32_t blo = f2u(clamp_lo), bhi = f2u(1.0f);
+  uint32_t start = blo;  // bit pattern of the first x of the current cell
+  for (uint32_t c = first; c <= last; c++) {
+    if (cell_of(u2f(start)) != c) return false;  // an empty cell: the bias is too small for this resolution
+    // one past the last x of cell c: bisection over the (monotone) cell index
+    uint32_t end;
+    if (c == last) {
+      end = bhi + 1;
+    } else {
+      uint32_t lo = start, hi = bhi;  // cell_of(lo) == c < cell_of(hi)
+      while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (cell_of(u2f(mid)) > c) hi = mid; else lo = mid;
+      }
+      end = hi;
+    }
+    const uint32_t base = (uint32_t) fn.eval(u2f(start));
+    const int cnt = fn.eval(u2f(end - 1)) - (int) base;
+    if (cnt > 1) return false;
+    const uint32_t tb = cnt == 1 ? f2u(fn.thr[base + 1]) : end;
+    // the add trick: (2^24 - tb + bits(x)) must stay inside [0, 2^25) for every x of the cell
+    if (tb - start > (1u << 24) || (cnt == 1 && (end - 1) - tb >= (1u << 24))) return false;
+    out->entries[c - first] = (base << 24) + (1u << 24) - tb;
+    start = end;
+  }
+  return true;
+}
+
+int biased_log_lut_eval(const BiasedLogLut &lut, float x) {
+  const float xc = x > lut.clamp_lo ? x : lut.clamp_lo;
+  const float u = xc + lut.bias;
+  return (int) ((lut.entries[(f2u(u) >> 16) - lut.first] + f2u(xc)) >> 24);
+}
+
 int build_cell_lut_auto(const StepFn &fn, int lo, int hi, CellLut *out) {
   for (int n = lo; n <= hi; n++)
     if (build_cell_lut(fn, n, out)) return n;

@@ -79,6 +79,26 @@ struct LogLut {
 bool build_log_lut(const StepFn &fn, LogLut *out);
 int log_lut_eval(const LogLut &lut, float x);
 
+// ---- biased log-cell LUT -----------------------------------------------------------------
+// The log-cell idea with the cell taken from u = x + bias (one extra float add) instead of x itself:
+//     xc   = max(x, clamp_lo)
+//     u    = xc + bias                              (float32, round to nearest)
+//     code = (entries[(bits(u) >> 16) - first] + bits(xc)) >> 24
+// Adding a constant is monotone, so every cell is still an interval of x; below the bias the cells become
+// uniform (width bias * 2^-7) instead of shrinking with x, which is all the sRGB encode needs there (its
+// thresholds are 1/3295 apart on the linear toe).  With bias = 2^-5 the pure sRGB encode takes 5 binades of u
+// = 644 cells instead of 1634, so a replica per lane (bank-conflict free for any content) fits shared memory
+// next to the other tables: 82 KB instead of 209 KB.
+struct BiasedLogLut {
+  float clamp_lo = 0.f;
+  float bias = 0.f;
+  uint32_t first = 0;             // bits(clamp_lo + bias) >> 16
+  std::vector<uint32_t> entries;  // (bits(1.0f + bias) >> 16) - first + 1 words
+};
+// Fails (returns false) if some cell would hold two thresholds or span more than the add trick allows.
+bool build_biased_log_lut(const StepFn &fn, float bias, BiasedLogLut *out);
+int biased_log_lut_eval(const BiasedLogLut &lut, float x);
+
 // ---- matrix constants, computed in float32 exactly as BT709.h:389-397 ------------------
 struct MatrixConsts {
   float inv255;  // 1.0f/255.0f
