@@ -35,6 +35,11 @@ struct bt709_ctx {
   float dec_log_clamp = 0.f;
   int dec_log_cells = 0;
   unsigned dec_log_first = 0;
+  // biased log-cell form of the same step function (645 cells: a replica per lane fits next to other tables)
+  const uint32_t *dec_blog_lut = nullptr;
+  float dec_blog_clamp = 0.f, dec_blog_bias = 0.f;
+  int dec_blog_cells = 0;
+  unsigned dec_blog_first = 0;
   // BT709_from_linear: linear float -> byte in gamma g (g = APPLE, SRGB, LINEAR)
   const uint32_t *fl_lut[3] = {};
   float fl_clamp[3] = {};
@@ -126,7 +131,7 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
 
   // ---- build every table on the host, once
   BlobBuilder blob;
-  size_t off_dec[5], off_fl[3], off_lin[3], off_comp[3][3], off_e444[5] = {}, off_log = 0;
+  size_t off_dec[5], off_fl[3], off_lin[3], off_comp[3][3], off_e444[5] = {}, off_log = 0, off_blog = 0;
   for (int g = 0; g < 5; g++) {
     StepFn fn;
     CellLut lut;
@@ -145,6 +150,14 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
       ctx->dec_log_cells = (int) llut.entries.size();
       ctx->dec_log_first = llut.first;
       off_log = blob.add(llut.entries.data(), llut.entries.size());
+    }
+    BiasedLogLut blut;
+    if (g == kLinear && build_biased_log_lut(fn, 1.0f / 32.0f, &blut)) {  // optional as well
+      ctx->dec_blog_clamp = blut.clamp_lo;
+      ctx->dec_blog_bias = blut.bias;
+      ctx->dec_blog_cells = (int) blut.entries.size();
+      ctx->dec_blog_first = blut.first;
+      off_blog = blob.add(blut.entries.data(), blut.entries.size());
     }
   }
   for (int g = 0; g < 3; g++) {
@@ -185,6 +198,7 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
   const uint32_t *base = (const uint32_t *) ctx->dev_blob;
   for (int g = 0; g < 5; g++) ctx->dec_lut[g] = base + off_dec[g];
   if (ctx->dec_log_cells) ctx->dec_log_lut = base + off_log;
+  if (ctx->dec_blog_cells) ctx->dec_blog_lut = base + off_blog;
   for (int g = 0; g < 3; g++) {
     ctx->fl_lut[g] = base + off_fl[g];
     ctx->lin256[g] = (const float *) (base + off_lin[g]);
@@ -258,6 +272,10 @@ int bt709_decode_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane
     a.log_lut = ctx->dec_log_lut; a.log_clamp_lo = ctx->dec_log_clamp;
     a.log_cells = ctx->dec_log_cells; a.log_first = ctx->dec_log_first;
   }
+  if ((int) gamma == (int) kLinear && ctx->dec_blog_lut) {
+    a.blog_lut = ctx->dec_blog_lut; a.blog_clamp_lo = ctx->dec_blog_clamp; a.blog_bias = ctx->dec_blog_bias;
+    a.blog_cells = ctx->dec_blog_cells; a.blog_first = ctx->dec_blog_first;
+  }
   a.m = ctx->m;
   a.one = 1.0f;
   const unsigned long long l0 = launches_begin();
@@ -287,6 +305,8 @@ int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, in
   // the decoder's Linear-mode step function IS the sRGB encode (decode_code(kLinear) == from_linear_code(kSrgb))
   a.enc_log_lut = ctx->dec_log_lut; a.enc_log_clamp_lo = ctx->dec_log_clamp;
   a.enc_log_cells = ctx->dec_log_cells; a.enc_log_first = ctx->dec_log_first;
+  a.enc_blog_lut = ctx->dec_blog_lut; a.enc_blog_clamp_lo = ctx->dec_blog_clamp; a.enc_blog_bias = ctx->dec_blog_bias;
+  a.enc_blog_cells = ctx->dec_blog_cells; a.enc_blog_first = ctx->dec_blog_first;
   a.one = 1.0f;
   const unsigned long long l0 = launches_begin();
   return finish(ctx, l0, launch_rescale(a, ctx->sm_count, stream), stream, wait);

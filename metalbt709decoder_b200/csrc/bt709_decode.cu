@@ -33,6 +33,7 @@ namespace bt709 {
 // loop-invariant packed constants {k, k}
 struct DecodeK2 {
   f32x2 kY, kC, inv255, ys, g_cb, b_cb, r_cr, g_cr, fN, magic, one;
+  f32x2 bias;  // CL2 < 0 only (biased log cells)
 };
 // two LUT lookups at once: clamp (scalar), index (packed FFMA2.RZ), two LDS, two adds.
 // returns the two sums whose byte 3 is the 8-bit code
@@ -41,10 +42,12 @@ __device__ __forceinline__ void lut2(float xa, float xb, float clamp_lo, const D
                                      uint32_t &sa, uint32_t &sb) {
   float ca = fmaxf(xa, clamp_lo), cb = fmaxf(xb, clamp_lo);
   uint32_t ta, tb;
-  if (CL2 == 0) {  // log-spaced cells: the index is the upper half of the float (sign, exponent, 7 mantissa bits)
+  if (CL2 <= 0) {  // log-spaced cells: the index is the upper half of the float (sign, exponent, 7 mantissa bits)
+    float ua = ca, ub = cb;
+    if (CL2 < 0) upk(add2(pk(ca, cb), k.bias), ua, ub);  // biased log cells: the cell of x + bias (one packed add per pair)
     // PRMT, not a shift: ptxas merges (x >> 16) << 7 into SHF + LOP3 + IADD, this stays PRMT + LEA
-    ta = __byte_perm(__float_as_uint(ca), 0, 0x4432);
-    tb = __byte_perm(__float_as_uint(cb), 0, 0x4432);
+    ta = __byte_perm(__float_as_uint(ua), 0, 0x4432);
+    tb = __byte_perm(__float_as_uint(ub), 0, 0x4432);
   } else {
     upku(fma2_rz(pk(ca, cb), k.fN, k.magic), ta, tb);
   }
@@ -184,6 +187,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) 
   k.fN = pk((float) N, (float) N);
   k.magic = pk(8388608.0f, 8388608.0f);
   k.one = pk(p.one, p.one);
+  k.bias = pk(0.0f, 0.0f);
 
   // this warp's place in the CTA's band: fixed for the whole kernel
   const unsigned r_local = warp / p.tiles_per_row;
@@ -282,6 +286,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
   k.fN = pk((float) N, (float) N);
   k.magic = pk(8388608.0f, 8388608.0f);
   k.one = pk(p.one, p.one);
+  k.bias = pk(0.0f, 0.0f);
 
   // this warp's first tile: band layout (fixed tile column, the row pair steps) or linear tile order (the
   // tile column steps and wraps into the next row pair; WRAP only, one tall image: see DecodeArgs.linear_tiles)
@@ -390,8 +395,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
 template <int CL2, int RL2, bool ALPHA, int D, bool COMPACT>
 __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   extern __shared__ __align__(128) uint32_t s_lut[];
-  constexpr int N = 1 << CL2, R = 1 << RL2;
-  const int entries = CL2 ? N + 1 : p.log_cells;
+  constexpr int N = CL2 > 0 ? 1 << CL2 : 1, R = 1 << RL2;
+  const int entries = CL2 > 0 ? N + 1 : p.log_cells;  // CL2 == 0: log cells, CL2 < 0: biased log cells
   const uint32_t kLutBytes = ((uint32_t) entries * R * 4 + 127u) & ~127u;
   // Y0 | Y1 | CbCr | pad (| A0 | A1 | pad | pad), 128 B each; COMPACT: without the pads
   constexpr uint32_t kStage = COMPACT ? (ALPHA ? 640 : 384) : (ALPHA ? 1024 : 512), kAlphaOff = COMPACT ? 384 : 512;
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   const int lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
   const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_lut);
-  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - ((CL2 ? 0x4B000000u : p.log_first) << (2 + RL2));
+  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - ((CL2 > 0 ? 0x4B000000u : p.log_first) << (2 + RL2));
   const uint32_t ring = smem0 + kLutBytes + warp * (D * kStage);
   const float clamp_lo = p.clamp_lo;
   DecodeK2 k;
@@ -416,6 +421,7 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   k.fN = pk((float) N, (float) N);
   k.magic = pk(8388608.0f, 8388608.0f);
   k.one = pk(p.one, p.one);
+  k.bias = pk(p.log_bias, p.log_bias);
 
   const unsigned g = blockIdx.x * (unsigned) p.lin_wpc + warp;
   if (g >= (unsigned) p.lin_warps) return;
@@ -576,6 +582,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_bulk(const DecodeArgs p) 
   k.fN = pk((float) N, (float) N);
   k.magic = pk(8388608.0f, 8388608.0f);
   k.one = pk(p.one, p.one);
+  k.bias = pk(0.0f, 0.0f);
 
   if (warp >= nwarps_active) return;  // spare warps
   const unsigned rows2 = p.rows2, rps = p.rps, w = p.w;
@@ -838,7 +845,7 @@ static bool bulk_ok(const DecodeArgs &a, int *nstages, int *stage_bytes, int *nr
 }
 
 #ifndef BT709_LIN_DEPTH
-#define BT709_LIN_DEPTH 2
+#define BT709_LIN_DEPTH 3
 #endif
 constexpr int kLinDepth = BT709_LIN_DEPTH;  // stages of the per-warp cp.async ring of k_decode_lin
 
@@ -849,7 +856,7 @@ static int launch_decode_lin(const DecodeArgs &a0, int sm_count, cudaStream_t s)
   a.h *= a.nframes;
   a.rows2 *= a.nframes;
   a.nframes = 1;
-  const size_t lut_bytes = (((size_t) (CL2 ? (1 << CL2) + 1 : a.log_cells) * (1 << RL2) * 4) + 127) & ~(size_t) 127;
+  const size_t lut_bytes = (((size_t) (CL2 > 0 ? (1 << CL2) + 1 : a.log_cells) * (1 << RL2) * 4) + 127) & ~(size_t) 127;
   if (lut_bytes >= kMaxDynSmem) return -1;
   const size_t slice = (size_t) kLinDepth * (COMPACT ? (ALPHA ? 640 : 384) : (ALPHA ? 1024 : 512));
   int wpc = (int) ((kMaxDynSmem - lut_bytes) / slice);
@@ -886,6 +893,18 @@ static int try_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s) {
   // steps per warp with a full grid of 32-warp CTAs
   const unsigned long long tiles = (unsigned long long) a.nframes * a.rows2 * a.tiles_per_row;
   const bool small = tiles <= (unsigned long long) small_steps * sm_count * 32;
+  static const bool no_blog = getenv("BT709_NO_BLOG") != nullptr;
+  if (a.blog_lut && a.blog_cells > 0 && !no_blog) {
+    // Linear mode, biased log cells: 645 cells, so a replica per lane leaves room for all 32 padded ring slices
+    DecodeArgs b = a;
+    b.lut = a.blog_lut;
+    b.clamp_lo = a.blog_clamp_lo;
+    b.log_cells = a.blog_cells;
+    b.log_first = a.blog_first;
+    b.log_bias = a.blog_bias;
+    if (small) return launch_decode_lin<-1, 2, ALPHA, false>(b, sm_count, s);
+    return launch_decode_lin<-1, 5, ALPHA, false>(b, sm_count, s);
+  }
   if (a.log_lut && a.log_cells > 0) {
     DecodeArgs b = a;
     b.lut = a.log_lut;
@@ -1025,6 +1044,12 @@ static int optin_decode_smem_log() {
                                  (int) kMaxDynSmem);
   if (e) return e;
   e = (int) cudaFuncSetAttribute(k_decode_lin<0, 2, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<-1, 5, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<-1, 2, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int) kMaxDynSmem);
   if (e) return e;
   e = (int) cudaFuncSetAttribute(k_decode_lin<10, 5, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -129,6 +129,14 @@ __device__ __forceinline__ f32x2 fma2_rn(f32x2 a, f32x2 b, f32x2 c) {
   return r;
 }
 
+// x + 32768.5 rounded toward zero, packed: the integer part of each (non-negative, < 32768) lane lands in byte 1
+__device__ __forceinline__ f32x2 add2_rz_pair(f32x2 a) {
+  f32x2 r, k;
+  asm("mov.b64 %0, {%1, %1};" : "=l"(k) : "r"(0x47000080u));
+  asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(k));
+  return r;
+}
+
 template <int K>
 __device__ __forceinline__ uint32_t magic_byte(uint32_t word) {  // bits of the float 2^23 + byte K
   return __byte_perm(word, 0x4B000000u, 0x7540 + K);

@@ -42,6 +42,13 @@ struct DecodeArgs {
   float log_clamp_lo;
   int log_cells;
   unsigned log_first;
+  // optional biased log-cell LUT of the same step function (bt709_tables.h: BiasedLogLut); nullptr = none.
+  // k_decode_lin<-1, ...> reads it through lut / clamp_lo / log_cells / log_first with log_bias set.
+  const uint32_t *blog_lut;
+  float blog_clamp_lo, blog_bias;
+  int blog_cells;
+  unsigned blog_first;
+  float log_bias;
   MatrixConsts m;
   float one;  // 1.0f, deliberately a runtime value (see decode_row)
 };
@@ -61,6 +68,11 @@ struct RescaleArgs {
   float enc_log_clamp_lo;
   int enc_log_cells;
   unsigned enc_log_first;
+  // optional biased log-cell form (bt709_tables.h: BiasedLogLut), one replica per lane in k_rescale_pair
+  const uint32_t *enc_blog_lut;
+  float enc_blog_clamp_lo, enc_blog_bias;
+  int enc_blog_cells;
+  unsigned enc_blog_first;
   float one;  // 1.0f, deliberately a runtime value (blocks FFMA2 contraction, see k_rescale_cols)
 };
 

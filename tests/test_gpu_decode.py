@@ -251,7 +251,8 @@ print("bulk ok")
     assert r.returncode == 0 and "bulk ok" in r.stdout, r.stdout + r.stderr
 
 
-@pytest.mark.parametrize("switch", ["BT709_NO_RING", "BT709_NO_LINEAR", "BT709_NO_COLS2", "BT709_NO_ELOG"])
+@pytest.mark.parametrize("switch", ["BT709_NO_RING", "BT709_NO_LINEAR", "BT709_NO_COLS2", "BT709_NO_ELOG", "BT709_NO_PAIR",
+                                    "BT709_NO_BLOG"])
 def test_superseded_kernel_variants_still_match(switch):
     """the variants kept for reproduction (band layout, register-prefetch decode, one-column
     rescale, uniform-cell encode LUT) are selected per process by an environment variable; each must stay exact"""

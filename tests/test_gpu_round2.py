@@ -341,3 +341,43 @@ def test_host_layer_mixes_caller_streams_and_internal_streams():
         t.release()
     dec.release()
     mrc.release()
+
+
+# ------------------------------------------------------------------ pass 2: paired-column kernel (k_rescale_pair)
+@pytest.mark.parametrize("mode", ["opaque", "mixed", "alpha"])
+@pytest.mark.parametrize("iw,ih,ow,oh,F", [(192, 108, 256, 144, 3), (300, 200, 300, 200, 2), (64, 48, 200, 150, 2),
+                                          (130, 70, 131, 141, 2), (640, 360, 1280, 720, 2), (96, 500, 97, 650, 1)])
+def test_rescale_paired_columns_opaque_speculation(mode, iw, ih, ow, oh, F):
+    """k_rescale_pair drops the alpha channel while every tap it sees has A = 255 and redoes a tile with the
+    four-channel code as soon as one does not; the next tiles of that warp then start on the alpha code and fall
+    back to the opaque code on the first fully opaque tile.  Opaque, fully translucent and mixed inputs (a few
+    translucent patches, so that both switches happen inside one launch) must all match the oracle."""
+    from _gpu import ctx, dev
+    rng = np.random.default_rng(77)
+    srcs = []
+    for f in range(F):
+        a = 255 if mode in ("opaque", "mixed") else None
+        src = bgra_random(iw, ih, seed=300 + f, alpha=a)
+        if mode == "mixed":
+            for _ in range(3):
+                x0, y0 = int(rng.integers(0, iw)), int(rng.integers(0, ih))
+                src[y0:y0 + 7, x0:x0 + 5, 3] = rng.integers(0, 255, src[y0:y0 + 7, x0:x0 + 5, 3].shape, dtype=np.uint8)
+        srcs.append(src)
+    tin = torch.stack([dev(s_) for s_ in srcs])
+    out = torch.zeros((F, oh, ow, 4), dtype=torch.uint8, device="cuda")
+    ctx().rescale_bgra(tin, out, wait=True)
+    got = out.cpu().numpy()
+    for f in range(F):
+        want = ORA.rescale_bgra(srcs[f], ow, oh)
+        assert np.array_equal(got[f], want), f"{mode} {iw}x{ih}->{ow}x{oh} frame {f}: {(got[f] != want).sum()} byte mismatches"
+        if mode == "opaque":
+            assert (got[f][..., 3] == 255).all()
+
+
+def test_rescale_1080p_to_1440p_opaque_full_size():
+    """BASELINE configs[1] pass 2 at full size on what pass 1 hands over (A = 255)"""
+    from _gpu import ctx, dev
+    src = bgra_random(1920, 1080, seed=31, alpha=255)
+    out = torch.zeros((1, 1440, 2560, 4), dtype=torch.uint8, device="cuda")
+    ctx().rescale_bgra(dev(src)[None], out, wait=True)
+    assert np.array_equal(out[0].cpu().numpy(), ORA.rescale_bgra(src, 2560, 1440))
