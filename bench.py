@@ -250,6 +250,10 @@ def make_batch(torch, w, h, frames, seed, kind):
         d["out"] = torch.empty((frames, h, w, 4), dtype=torch.uint8, device="cuda")
     if kind == "alpha":
         d["a"] = torch.randint(16, 236, (frames, h, w), dtype=torch.uint8, device="cuda", generator=g)
+    if kind == "fused":
+        # work area of the fused kernel (the reference's _resizeTexture argument): ~60 MB of it are used, as per-SM
+        # slices that stay in L2; the intermediate image is never written out
+        d["scratch"] = torch.empty((frames, h, w, 4), dtype=torch.uint8, device="cuda")
     if kind in ("rescale", "twopass", "fused"):
         if kind == "rescale":
             d["src"] = torch.randint(0, 256, (frames, h, w, 4), dtype=torch.uint8, device="cuda", generator=g)
@@ -294,7 +298,7 @@ def make_step(ctx, d, kind, gamma, stream):
             ctx.rescale_bgra(d["out"], d["big"], stream=stream)
         return two
     if kind == "fused":
-        return lambda: ctx.decode_rescale_nv12(gamma, d["y"], d["c"], None, d["big"], stream=stream)
+        return lambda: ctx.decode_rescale_nv12(gamma, d["y"], d["c"], d["scratch"], d["big"], stream=stream)
     if kind == "encode":
         return lambda: ctx.encode_bgra_to_nv12(1, 0, d["src"], d["y"], d["c"], stream=stream)
     raise ValueError(kind)

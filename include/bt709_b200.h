@@ -126,9 +126,14 @@ BT709_API int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *bgra_i
                                  void *stream, int wait);
 
 /* The per-frame policy of -[AAPLRenderer drawInMTKView:] (AAPLRenderer.m:891-977):
- * output size == frame size -> pass 1 straight into bgra_out; otherwise pass 1 into the
- * same-size sRGB intermediate `scratch` (the reference's _resizeTexture) and pass 2 into
- * bgra_out.  `scratch` may be NULL only in the same-size case. */
+ * output size == frame size -> pass 1 straight into bgra_out; otherwise decode + rescale into bgra_out.
+ * `scratch` stands for the reference's same-size sRGB intermediate (_resizeTexture) and may be NULL only in the
+ * same-size case.  When the geometry allows it (no alpha stream, w a multiple of 128, even h, even out_w, no
+ * horizontal downscale, tightly packed scratch rows and frames) the two passes run FUSED in one kernel: each CTA
+ * decodes the source rows of one band of 64 output rows into a slice of `scratch` that it overwrites band after
+ * band (~60 MB in all, resident in L2), so the intermediate image never reaches HBM and `scratch` does NOT hold it
+ * afterwards.  The result is bit-identical either way.  Otherwise pass 1 writes the full intermediate into `scratch`
+ * and pass 2 reads it back (two kernels). */
 BT709_API int bt709_decode_rescale_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y,
                                         const bt709_plane *cbcr, const bt709_plane *alpha_y,
                                         const bt709_plane *scratch, const bt709_plane *bgra_out, int w,

@@ -245,6 +245,11 @@ const char *bt709_status_string(int s) {
   }
 }
 
+static void fill_decode_args(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y, const bt709_plane *cbcr,
+                             const bt709_plane *alpha_y, const bt709_plane *bgra_out, int w, int h, int nframes, DecodeArgs *pa);
+static void fill_rescale_args(const bt709_ctx *ctx, const bt709_plane *in, int in_w, int in_h, const bt709_plane *out, int out_w,
+                              int out_h, int nframes, RescaleArgs *pa);
+
 int bt709_decode_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y, const bt709_plane *cbcr,
                       const bt709_plane *alpha_y, const bt709_plane *bgra_out, int w, int h, int nframes,
                       void *stream, int wait) {
@@ -262,22 +267,7 @@ int bt709_decode_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane
   DeviceGuard guard(ctx->device);
   if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
   DecodeArgs a{};
-  a.y = (const uint8_t *) y->ptr; a.py = (long long) y->pitch; a.sy = (long long) y->frame_stride;
-  a.c = (const uint8_t *) cbcr->ptr; a.pc = (long long) cbcr->pitch; a.sc = (long long) cbcr->frame_stride;
-  a.out = (uint8_t *) bgra_out->ptr; a.po = (long long) bgra_out->pitch; a.so = (long long) bgra_out->frame_stride;
-  if (alpha_y) { a.a = (const uint8_t *) alpha_y->ptr; a.pa = (long long) alpha_y->pitch; a.sa = (long long) alpha_y->frame_stride; }
-  a.w = w; a.h = h; a.nframes = nframes;
-  a.lut = ctx->dec_lut[gamma]; a.clamp_lo = ctx->dec_clamp[gamma]; a.cells_log2 = ctx->dec_cells[gamma];
-  if ((int) gamma == (int) kLinear && ctx->dec_log_lut) {
-    a.log_lut = ctx->dec_log_lut; a.log_clamp_lo = ctx->dec_log_clamp;
-    a.log_cells = ctx->dec_log_cells; a.log_first = ctx->dec_log_first;
-  }
-  if ((int) gamma == (int) kLinear && ctx->dec_blog_lut) {
-    a.blog_lut = ctx->dec_blog_lut; a.blog_clamp_lo = ctx->dec_blog_clamp; a.blog_bias = ctx->dec_blog_bias;
-    a.blog_cells = ctx->dec_blog_cells; a.blog_first = ctx->dec_blog_first;
-  }
-  a.m = ctx->m;
-  a.one = 1.0f;
+  fill_decode_args(ctx, gamma, y, cbcr, alpha_y, bgra_out, w, h, nframes, &a);
   const unsigned long long l0 = launches_begin();
   return finish(ctx, l0, launch_decode(a, ctx->sm_count, stream), stream, wait);
 }
@@ -295,7 +285,37 @@ int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, in
   DeviceGuard guard(ctx->device);
   if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
   RescaleArgs a{};
-  a.in = (const uint8_t *) in->ptr; a.pi = (long long) in->pitch; a.si = (long long) in->frame_stride;
+  fill_rescale_args(ctx, in, in_w, in_h, out, out_w, out_h, nframes, &a);
+  const unsigned long long l0 = launches_begin();
+  return finish(ctx, l0, launch_rescale(a, ctx->sm_count, stream), stream, wait);
+}
+
+// fills the kernel argument structs shared by the one-pass, two-pass and fused entries
+static void fill_decode_args(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y, const bt709_plane *cbcr,
+                             const bt709_plane *alpha_y, const bt709_plane *bgra_out, int w, int h, int nframes, DecodeArgs *pa) {
+  DecodeArgs &a = *pa;
+  a.y = (const uint8_t *) y->ptr; a.py = (long long) y->pitch; a.sy = (long long) y->frame_stride;
+  a.c = (const uint8_t *) cbcr->ptr; a.pc = (long long) cbcr->pitch; a.sc = (long long) cbcr->frame_stride;
+  if (bgra_out) { a.out = (uint8_t *) bgra_out->ptr; a.po = (long long) bgra_out->pitch; a.so = (long long) bgra_out->frame_stride; }
+  if (alpha_y) { a.a = (const uint8_t *) alpha_y->ptr; a.pa = (long long) alpha_y->pitch; a.sa = (long long) alpha_y->frame_stride; }
+  a.w = w; a.h = h; a.nframes = nframes;
+  a.lut = ctx->dec_lut[gamma]; a.clamp_lo = ctx->dec_clamp[gamma]; a.cells_log2 = ctx->dec_cells[gamma];
+  if ((int) gamma == (int) kLinear && ctx->dec_log_lut) {
+    a.log_lut = ctx->dec_log_lut; a.log_clamp_lo = ctx->dec_log_clamp;
+    a.log_cells = ctx->dec_log_cells; a.log_first = ctx->dec_log_first;
+  }
+  if ((int) gamma == (int) kLinear && ctx->dec_blog_lut) {
+    a.blog_lut = ctx->dec_blog_lut; a.blog_clamp_lo = ctx->dec_blog_clamp; a.blog_bias = ctx->dec_blog_bias;
+    a.blog_cells = ctx->dec_blog_cells; a.blog_first = ctx->dec_blog_first;
+  }
+  a.m = ctx->m;
+  a.one = 1.0f;
+}
+
+static void fill_rescale_args(const bt709_ctx *ctx, const bt709_plane *in, int in_w, int in_h, const bt709_plane *out, int out_w,
+                              int out_h, int nframes, RescaleArgs *pa) {
+  RescaleArgs &a = *pa;
+  if (in) { a.in = (const uint8_t *) in->ptr; a.pi = (long long) in->pitch; a.si = (long long) in->frame_stride; }
   a.out = (uint8_t *) out->ptr; a.po = (long long) out->pitch; a.so = (long long) out->frame_stride;
   a.iw = in_w; a.ih = in_h; a.ow = out_w; a.oh = out_h; a.nframes = nframes;
   a.scale_x = (float) in_w / (float) out_w;
@@ -308,8 +328,6 @@ int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, in
   a.enc_blog_lut = ctx->dec_blog_lut; a.enc_blog_clamp_lo = ctx->dec_blog_clamp; a.enc_blog_bias = ctx->dec_blog_bias;
   a.enc_blog_cells = ctx->dec_blog_cells; a.enc_blog_first = ctx->dec_blog_first;
   a.one = 1.0f;
-  const unsigned long long l0 = launches_begin();
-  return finish(ctx, l0, launch_rescale(a, ctx->sm_count, stream), stream, wait);
 }
 
 int bt709_decode_rescale_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y, const bt709_plane *cbcr,
@@ -320,6 +338,26 @@ int bt709_decode_rescale_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt7
     return bt709_decode_nv12(ctx, gamma, y, cbcr, alpha_y, bgra_out, w, h, nframes, stream, wait);
   if (!ctx) return BT709_E_NULL;
   if (!scratch || !scratch->ptr) return BT709_E_SCRATCH;
+  // ---- fused: one kernel, the intermediate stays in L2.  Same validation as the two calls
+  // below would do; `scratch` is used as a raw work area, so only when its rows and frames are tightly packed.
+  if (plane_ok(y) && plane_ok(cbcr) && plane_ok(bgra_out) && !alpha_y && w > 0 && h > 0 && out_w > 0 && out_h > 0 &&
+      nframes > 0 && (int) gamma >= 0 && (int) gamma <= 3 && scratch->pitch == (size_t) w * 4 &&
+      (nframes == 1 || scratch->frame_stride == scratch->pitch * (size_t) h)) {
+    const size_t cw2 = (size_t) ((w + 1) / 2) * 2, ch = (size_t) (h + 1) / 2;
+    int rc;
+    if ((rc = check_plane(y, w, h, nframes))) return rc;
+    if ((rc = check_plane(cbcr, cw2, ch, nframes))) return rc;
+    if ((rc = check_plane(bgra_out, (size_t) out_w * 4, out_h, nframes))) return rc;
+    DeviceGuard guard(ctx->device);
+    if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
+    DecodeArgs d{};
+    RescaleArgs r{};
+    fill_decode_args(ctx, gamma, y, cbcr, nullptr, nullptr, w, h, nframes, &d);
+    fill_rescale_args(ctx, nullptr, w, h, bgra_out, out_w, out_h, nframes, &r);
+    const unsigned long long l0 = launches_begin();
+    const int e = launch_fused(d, r, (uint8_t *) scratch->ptr, scratch->pitch * (size_t) h * (size_t) nframes, ctx->sm_count, stream);
+    if (e != -1) return finish(ctx, l0, e, stream, wait);
+  }
   // AAPLRenderer.m:940-977: decode into the same-size sRGB intermediate, then rescale
   int rc = bt709_decode_nv12(ctx, gamma, y, cbcr, alpha_y, scratch, w, h, nframes, stream, 0);
   if (rc) return rc;

@@ -117,6 +117,19 @@ struct PlanarArgs {
   int cw, ch, nframes;
 };
 
+// Fused decode -> rescale (bt709_fused.cu): one persistent CTA per SM takes (frame, band of 64 output rows) units;
+// it decodes the band's source rows into its own slice of `scratch` (a few hundred KB that it overwrites band after
+// band, so the lines live in L2 and the intermediate image never reaches HBM) and then runs the paired-column
+// walker of pass 2 over them.
+struct FusedArgs {
+  DecodeArgs d;       // NV12 source (opaque: no alpha plane), gamma tables
+  RescaleArgs r;      // iw/ih = frame size, ow/oh/out = destination, encode tables (in/pi/si unused)
+  uint8_t *scratch;   // device memory, gridDim.x * cta_stride bytes
+  long long cta_stride;
+  unsigned spitch;    // bytes per scratch row (>= w * 4, multiple of 16)
+  int bands;          // ceil(oh / 64)
+};
+
 // number of kernels the calling thread has launched through the launchers below (bt709_launch_count accounting)
 extern thread_local unsigned long long tl_kernel_launches;
 inline void note_launch() { ++tl_kernel_launches; }
@@ -124,6 +137,10 @@ inline void note_launch() { ++tl_kernel_launches; }
 // launchers (one per kernel family).  Each returns the cudaError_t of the launch.
 int launch_decode(const DecodeArgs &a, int sm_count, void *stream);
 int launch_rescale(const RescaleArgs &a, int sm_count, void *stream);
+// fused decode -> rescale; scratch_bytes: size of the caller's scratch area.  Returns -1 when the fused kernel does not
+// apply (geometry, alignment, alpha stream, scratch too small): the caller then runs the two passes.
+int launch_fused(const DecodeArgs &d, const RescaleArgs &r, uint8_t *scratch, size_t scratch_bytes, int sm_count, void *stream);
+int fused_kernels_init();
 int launch_encode(const EncodeArgs &a, int sm_count, void *stream);
 int launch_convert444(const Packed444Args &a, void *stream);
 int launch_unconvert444(const Packed444Args &a, void *stream);

@@ -113,6 +113,7 @@ int kernels_init() {
   int e;
   if ((e = decode_kernels_init())) return e;
   if ((e = rescale_kernels_init())) return e;
+  if ((e = fused_kernels_init())) return e;  // after the rescale init: it probes where dynamic shared memory starts
   return encode_kernels_init();
 }
 

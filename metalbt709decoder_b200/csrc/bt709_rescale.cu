@@ -1,6 +1,6 @@
 // bt709_rescale.cu — pass 2: bilinear resample of an sRGB BGRA8 image in linear light
 // (samplingShader, AAPLShaders.metal:73-85 + MetalScaleRenderContext.m:55-105).
-#include "bt709_device.cuh"
+#include "bt709_pair.cuh"
 
 namespace bt709 {
 
@@ -86,11 +86,6 @@ __global__ void __launch_bounds__(256) k_rescale(const RescaleArgs p) {
 // The oracle's clamp01 after the vertical blend is the identity for these operands (for a, b in
 // [0,1] and f in [0,1]: d = RN(b-a), p = RN(f*d), |p| <= |d|, and RN(a+p) stays inside [0,1] because
 // RN(1-a) <= (1-a) + 2^-25 and RN(a-b) <= a), so the blends run on packed FFMA2/FMUL2 without .sat.
-constexpr int kWalkTH = 64;       // output rows per warp tile
-constexpr int kWalkWarps = 32;    // warps per CTA, one CTA per SM
-constexpr int kWalkPD = 3;        // source rows fetched ahead of use
-constexpr int kWalkRowInfo = (kWalkTH + 1) * 4;  // words of row info per warp (one sentinel entry)
-
 struct Lin4 {
   f32x2 rg, ba;  // (R, G), (B, A) in linear light (A is linear already)
 };
@@ -459,225 +454,43 @@ __global__ void __launch_bounds__(kWalk2Warps * 32, 1) k_rescale_cols2(const Res
   }
 }
 
-// -------------------------------------------------------------- rescale, paired columns (round 2)
-// The two-column walker again, rebuilt around three measurements of k_rescale_cols2 (profiles/r01_rescale_cols_*):
-// 62 instructions per output pixel with issue slots 80 % busy, and 12 shared-memory wavefronts per 32 output pixels of
-// which the encode gathers are ~8 (16 LUT replicas: two lanes per replica collide on random content).
-//   * the output of pass 1 is opaque (A = 255, AAPLShaders.metal:243) unless an alpha stream was decoded, and a
-//     blend of 1.0 with 1.0 is 1.0 in every float32 step of the oracle: the alpha channel is dropped (no table
-//     gathers, no blends, no rounding) on a SPECULATIVE basis - every tap word is AND-ed into an accumulator, and if
-//     a warp finds a tap with A != 255 it redoes its tile with the four-channel code and starts the next tiles
-//     there (two LOP3 per source row is all the opaque case pays);
-//   * the packed pairs are (column a, column b) of ONE channel instead of (R, G) / (B, A) of one column: the table
-//     gathers land directly in pair registers, the horizontal blend takes the per-column fractions as one packed
-//     operand, and column b's taps are chosen by selecting the two texel WORDS (2 SEL) instead of four blended
-//     pairs (8 SEL);
-//   * the sRGB encode uses the biased log-cell LUT (bt709_tables.h): 645 cells, ONE REPLICA PER LANE (82 KB): a
-//     gather is a single conflict-free wavefront for any content, for one extra packed add per pair of lookups;
-//   * the alpha byte -> float step is arithmetic (PRMT + packed add + packed multiply), not a table.
-// Same row-info slices, unclamped row walk and three-row register prefetch queue as k_rescale_cols2.
-constexpr int kPairWarps = 24;
-
-struct PairCtx {
-  uint32_t lin_lane, rows_base, enc_base;
-  float clamp_lo;
-  f32x2 one, neg1, bias2, inv255_2, nmagic2;
-};
-
-struct H3 {
-  f32x2 r, g, b, a;  // (column a, column b) per channel, linear light; a only when ALPHA
-};
-
-// Layout (dynamic shared memory):
-//   [encode LUT, biased log cells: cell i replica r at word i*32 + r][pad][lin table at the next 64 KB boundary:
-//    word b*64 + r = sRGB byte b -> linear float, replica r; the upper 128 B of each 256-B entry are unused][row info]
-__device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s_mem) {
-  const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_mem);
-  const int nenc = p.enc_blog_cells << 5;
-  const uint32_t head = (uint32_t) (nenc + 4) * 4u;
-  const uint32_t pad = head + ((0x10000u - ((smem0 + head) & 0xFFFFu)) & 0xFFFFu);
-  float *s_lin = reinterpret_cast<float *>(s_mem + (pad >> 2));
-  uint32_t *s_rows = s_mem + (pad >> 2) + 256 * 64;
-  uint32_t *s_enc = s_mem + 4;
-  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_lin[(i >> 5) * 64 + (i & 31)] = __ldg(&p.lin256[i >> 5]);
-  for (int i = threadIdx.x; i < nenc; i += blockDim.x) s_enc[i] = __ldg(&p.enc_blog_lut[i >> 5]);
-  // (index register << 7) + enc_base, the index register holding first + cell: the bias goes through shared memory so
-  // that ptxas sees an opaque register and emits one LEA per lookup
-  if (threadIdx.x == 0) s_enc[-1] = (uint32_t) __cvta_generic_to_shared(s_enc) - (p.enc_blog_first << 7);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  PairCtx c;
-  c.lin_lane = (smem0 + pad) | (lane << 2);
-  c.rows_base = (uint32_t) __cvta_generic_to_shared(s_rows + warp * kWalkRowInfo);
-  c.enc_base = *reinterpret_cast<volatile uint32_t *>(s_enc - 1) + (lane << 2);
-  c.clamp_lo = p.enc_blog_clamp_lo;
-  c.one = pk(p.one, p.one);
-  c.neg1 = pk(-1.0f, -1.0f);
-  c.bias2 = pk(p.enc_blog_bias, p.enc_blog_bias);
-  c.inv255_2 = pk(1.0f / 255.0f, 1.0f / 255.0f);
-  c.nmagic2 = pk(-8388608.0f, -8388608.0f);
-  return c;
-}
-
-// One warp tile (64 output columns x kWalkTH output rows).  Returns true when every tap word it fetched had A = 255.
-template <bool ALPHA>
-__device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c, unsigned f, int tx, int ty, int lane) {
-  const uint32_t lin_lane = c.lin_lane, rows_base = c.rows_base, enc_base = c.enc_base;
-  const float clamp_lo = c.clamp_lo;
-  const f32x2 one = c.one, neg1 = c.neg1;
-  auto lin_of = [&](uint32_t px, uint32_t sel) -> float {
-    float v;
-    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(__byte_perm(px, lin_lane, sel)));  // table | byte << 8 | lane << 2
-    return v;
-  };
-  auto lerp = [&](f32x2 t0, f32x2 t1, f32x2 f2) -> f32x2 {  // t0 + f * (t1 - t0): the oracle's three rounded steps
-    return fma2_rn(mul2(f2, fma2_rn(t0, neg1, t1)), one, t0);
-  };
-  // two clamped values -> the two sums whose byte 3 is the sRGB code (biased log-cell LUT, one replica per lane)
-  auto enc2 = [&](f32x2 v, uint32_t &sa, uint32_t &sb) {
-    float va, vb, ua, ub;
-    upk(v, va, vb);
-    va = fmaxf(va, clamp_lo);
-    vb = fmaxf(vb, clamp_lo);
-    upk(add2(pk(va, vb), c.bias2), ua, ub);
-    uint32_t ea, eb;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(ea) : "r"((__byte_perm(__float_as_uint(ua), 0, 0x4432) << 7) + enc_base));
-    asm("ld.shared.u32 %0, [%1];" : "=r"(eb) : "r"((__byte_perm(__float_as_uint(ub), 0, 0x4432) << 7) + enc_base));
-    sa = ea + __float_as_uint(va);
-    sb = eb + __float_as_uint(vb);
-  };
-
-  const int oy0 = ty * kWalkTH;
-  __syncwarp();
-#pragma unroll
-  for (int k = 0; k < kWalkTH / 32; k++) {
-    const int r = k * 32 + lane, oy = oy0 + r;
-    const float sy = __fadd_rn(__fmul_rn(__fadd_rn((float) oy, 0.5f), p.scale_y), -0.5f);
-    const float fy0 = floorf(sy);
-    asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(rows_base + r * 16), "r"(__float_as_uint(__fsub_rn(sy, fy0))),
-                 "r"(oy < p.oh ? (uint32_t) (int) fy0 : 0x7fffffffu) : "memory");
-  }
-  if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1,%1};" ::"r"(rows_base + kWalkTH * 16), "r"(0x7fffffffu) : "memory");
-  __syncwarp();
-
-  const int ylast = p.ih - 1, xlast = p.iw - 1;
-  const unsigned pi = (unsigned) p.pi, po = (unsigned) p.po;
-  const int oxa = tx * 64 + lane * 2;
-  const bool live_a = oxa < p.ow, live_b = oxa + 1 < p.ow;
-  const float sxa = __fadd_rn(__fmul_rn(__fadd_rn((float) oxa, 0.5f), p.scale_x), -0.5f);
-  const float sxb = __fadd_rn(__fmul_rn(__fadd_rn((float) (oxa + 1), 0.5f), p.scale_x), -0.5f);
-  const float fxa0 = floorf(sxa), fxb0 = floorf(sxb);
-  const int xia = (int) fxa0, xib = (int) fxb0;  // xib - xia is 0 or 1 for scales <= 1
-  const bool bsel = xib != xia;                  // column b uses (T1, T2) instead of (T0, T1)
-  const f32x2 fx2 = pk(__fsub_rn(sxa, fxa0), __fsub_rn(sxb, fxb0));
-  const int p0 = min(max(xia, 0), xlast), p1 = min(max(xia + 1, 0), xlast), p2 = min(max(xia + 2, 0), xlast);
-  const unsigned d1 = (unsigned) (p1 - p0) * 4u, d2 = (unsigned) (p2 - p0) * 4u;
-  const uint8_t *src0 = p.in + (long long) f * p.si + (size_t) p0 * 4;
-  uint8_t *dp = p.out + (long long) f * p.so + (size_t) min(oxa, p.ow - 1) * 4 + (long long) (oy0 - 1) * (long long) po;
-  const bool wide_store = live_b && ((reinterpret_cast<uintptr_t>(dp) | po) & 7u) == 0;
-
-  uint32_t acc = 0xFFFFFFFFu;  // AND of every tap word: byte 3 stays 255 while the tile is opaque
-  const uint8_t *fp = nullptr;
-  auto fetch = [&](int row, uint32_t &w0, uint32_t &w1, uint32_t &w2) {
-    w0 = __ldg(reinterpret_cast<const uint32_t *>(fp));
-    w1 = __ldg(reinterpret_cast<const uint32_t *>(fp + d1));
-    w2 = __ldg(reinterpret_cast<const uint32_t *>(fp + d2));
-    fp += (unsigned) row < (unsigned) ylast ? pi : 0u;
-  };
-  auto blend = [&](uint32_t w0, uint32_t w1, uint32_t w2) -> H3 {
-    const uint32_t u0 = bsel ? w1 : w0, u1 = bsel ? w2 : w1;  // column b's taps
-    acc = acc & w0 & w1;
-    acc &= w2;
-    H3 h;
-    h.r = lerp(pk(lin_of(w0, 0x7624), lin_of(u0, 0x7624)), pk(lin_of(w1, 0x7624), lin_of(u1, 0x7624)), fx2);
-    h.g = lerp(pk(lin_of(w0, 0x7614), lin_of(u0, 0x7614)), pk(lin_of(w1, 0x7614), lin_of(u1, 0x7614)), fx2);
-    h.b = lerp(pk(lin_of(w0, 0x7604), lin_of(u0, 0x7604)), pk(lin_of(w1, 0x7604), lin_of(u1, 0x7604)), fx2);
-    if (ALPHA) {  // alpha is linear: byte * (1/255), exactly as the oracle's tap
-      const f32x2 a0 = mul2(add2(pku(magic_byte<3>(w0), magic_byte<3>(u0)), c.nmagic2), c.inv255_2);
-      const f32x2 a1 = mul2(add2(pku(magic_byte<3>(w1), magic_byte<3>(u1)), c.nmagic2), c.inv255_2);
-      h.a = lerp(a0, a1, fx2);
-    }
-    return h;
-  };
-
-  uint32_t ip = rows_base;
-  uint32_t info_fy, info_y;
-  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(info_fy), "=r"(info_y) : "r"(ip));
-  int y = (int) info_y;
-  uint32_t q0[kWalkPD], q1[kWalkPD], q2[kWalkPD], a0w, a1w, a2w;
-  fp = ptr_mad(src0, (unsigned) max(y, 0), pi);
-  fetch(y, a0w, a1w, a2w);
-#pragma unroll
-  for (int j = 0; j < kWalkPD; j++) fetch(y + 1 + j, q0[j], q1[j], q2[j]);
-  H3 H[2];
-  H[0] = blend(a0w, a1w, a2w);
-  bool done = false;
-  while (!done) {
-#pragma unroll
-    for (int j = 0; j < 2 * kWalkPD; j++) {
-      H[(j + 1) & 1] = blend(q0[j % kWalkPD], q1[j % kWalkPD], q2[j % kWalkPD]);
-      fetch(y + 1 + kWalkPD, q0[j % kWalkPD], q1[j % kWalkPD], q2[j % kWalkPD]);
-      while ((int) info_y <= y) {
-        dp += po;
-        const float fy = __uint_as_float(info_fy);
-        const f32x2 fy2 = pk(fy, fy);
-        const H3 &A = H[j & 1], &B = H[(j + 1) & 1];
-        uint32_t ra, rb, ga, gb, ba, bb;
-        enc2(lerp(A.r, B.r, fy2), ra, rb);
-        enc2(lerp(A.g, B.g, fy2), ga, gb);
-        enc2(lerp(A.b, B.b, fy2), ba, bb);
-        uint32_t wa, wb;
-        if (ALPHA) {
-          // round(255 * v), half away from zero: the integer part of RZ(x + 32768.5) sits in byte 1
-          uint32_t ta, tb;
-          // (the product goes through an FMA with +0 so that no multiply feeds the round-toward-zero add directly)
-          upku(add2_rz_pair(fma2_rn(lerp(A.a, B.a, fy2), pk(255.0f, 255.0f), pk(0.0f, 0.0f))), ta, tb);
-          wa = __byte_perm(__byte_perm(ba, ga, 0x0073), __byte_perm(ra, ta, 0x0053), 0x5410);
-          wb = __byte_perm(__byte_perm(bb, gb, 0x0073), __byte_perm(rb, tb, 0x0053), 0x5410);
-        } else {
-          wa = __byte_perm(__byte_perm(ba, ga, 0x0073), ra, 0x7710) | 0xFF000000u;
-          wb = __byte_perm(__byte_perm(bb, gb, 0x0073), rb, 0x7710) | 0xFF000000u;
-        }
-        if (wide_store) {
-          *reinterpret_cast<uint2 *>(dp) = make_uint2(wa, wb);
-        } else {
-          if (live_a) *reinterpret_cast<uint32_t *>(dp) = wa;
-          if (live_b) *reinterpret_cast<uint32_t *>(dp + 4) = wb;
-        }
-        ip += 16;
-        asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(info_fy), "=r"(info_y) : "r"(ip));
-      }
-      y++;
-      if (info_y == 0x7fffffffu) { done = true; break; }
-    }
-  }
-  return __all_sync(0xffffffffu, (acc >> 24) == 0xFFu);
-}
-
 __global__ void __launch_bounds__(kPairWarps * 32, 1) k_rescale_pair(const RescaleArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
   const PairCtx c = pair_tables(p, s_mem);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int tiles_x = (p.ow + 63) >> 6, tiles_y = (p.oh + kWalkTH - 1) / kWalkTH;
+  constexpr int TW = 64 * kPairNP;  // tile width
+  const int tiles_x = (p.ow + TW - 1) / TW, tiles_y = (p.oh + kWalkTH - 1) / kWalkTH;
   const unsigned tiles_per_frame = tiles_x * tiles_y;
   const unsigned tiles = (unsigned) p.nframes * tiles_per_frame;
   bool with_alpha = false;  // warp-uniform: the code this warp tries first on its next tile
   for (unsigned t = blockIdx.x * kPairWarps + warp; t < tiles; t += gridDim.x * kPairWarps) {
     const unsigned f = t / tiles_per_frame, tr = t - f * tiles_per_frame;
     const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+    const uint8_t *src = p.in + (long long) f * p.si;
+    uint8_t *dst = p.out + (long long) f * p.so;
+    const unsigned pi = (unsigned) p.pi;
+    const int ox0 = tx * TW, oy0 = ty * kWalkTH;
+    // the alpha code runs one pair per thread (a 64-column half tile at a time) to stay within the register budget
+    auto alpha_tile = [&]() -> bool {
+      bool opaque = true;
+#pragma unroll 1
+      for (int q = 0; q < kPairNP; q++)
+        if (ox0 + q * 64 < p.ow) opaque = pair_tile<true, true, 1>(p, c, src, pi, dst, ox0 + q * 64, oy0, lane) && opaque;
+      return opaque;
+    };
     if (!with_alpha) {
-      if (!pair_tile<false>(p, c, f, tx, ty, lane)) {  // a tap with A != 255: the tile needs the alpha channel
-        pair_tile<true>(p, c, f, tx, ty, lane);
+      if (!pair_tile<false, true, kPairNP>(p, c, src, pi, dst, ox0, oy0, lane)) {  // a tap with A != 255: redo with alpha
+        alpha_tile();
         with_alpha = true;
       }
     } else {
-      if (pair_tile<true>(p, c, f, tx, ty, lane)) with_alpha = false;  // opaque again
+      if (alpha_tile()) with_alpha = false;  // opaque again
     }
   }
 }
 
 // shared-memory address (low 16 bits matter) at which a kernel's dynamic shared memory starts; -1 = unknown
-static int g_dyn_smem_base = -1;
+int g_dyn_smem_base = -1;  // shared with bt709_fused.cu
 __global__ void k_probe_smem_base(unsigned *out) {
   extern __shared__ __align__(16) uint32_t s_mem[];
   *out = (unsigned) __cvta_generic_to_shared(s_mem);
@@ -690,8 +503,8 @@ static size_t elog_layout_bytes(unsigned base, int cells, int warps) {
 }
 
 // dynamic bytes k_rescale_pair needs: [LUT, 32 replicas][pad to 64 KB][table 64 KB][row info]
-static size_t pair_layout_bytes(unsigned base, int cells) {
-  const unsigned head = ((unsigned) cells * 32u + 4u) * 4u;
+size_t pair_layout_bytes(unsigned base, int cells, unsigned extra_bytes) {
+  const unsigned head = ((((unsigned) cells * 32u + 4u) * 4u + 127u) & ~127u) + extra_bytes;
   const unsigned pad = head + ((0x10000u - ((base + head) & 0xFFFFu)) & 0xFFFFu);
   return (size_t) pad + 65536u + (size_t) kPairWarps * kWalkRowInfo * 4u;
 }
@@ -727,13 +540,15 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
                                           a.iw <= a.ow && !no_cols2 ? kWalk2Warps : kWalkWarps) <= kMaxDynSmem;
       cudaStream_t st = (cudaStream_t) stream;
       static const bool no_pair = getenv("BT709_NO_PAIR") != nullptr;
-      if (a.iw <= a.ow && !no_pair && !no_cols2 && b.enc_blog_lut && g_dyn_smem_base >= 0 &&
-          pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells) <= kMaxDynSmem) {
+      // (even width and 8-byte aligned rows: every column pair is stored with one 8-byte store)
+      const bool pair_ok = (a.ow % 2 == 0) && aligned(a.out, 8) && aligned(a.po, 8) && aligned(a.so, 8);
+      if (a.iw <= a.ow && pair_ok && !no_pair && !no_cols2 && b.enc_blog_lut && g_dyn_smem_base >= 0 &&
+          pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0) <= kMaxDynSmem) {
         // horizontal scale <= 1: paired columns, opaque speculation, conflict-free encode LUT (k_rescale_pair)
-        const long long tiles64 = (long long) ((a.ow + 63) / 64) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
+        const long long tiles64 = (long long) ((a.ow + 64 * kPairNP - 1) / (64 * kPairNP)) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
         const long long ctas2 = (tiles64 + kPairWarps - 1) / kPairWarps;
         const unsigned g2 = (unsigned) (ctas2 < (long long) sm_count ? ctas2 : (long long) sm_count);
-        k_rescale_pair<<<g2, kPairWarps * 32, pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells), st>>>(b), note_launch();
+        k_rescale_pair<<<g2, kPairWarps * 32, pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0), st>>>(b), note_launch();
       } else if (a.iw <= a.ow && !no_cols2 && (elog || smem_u <= kMaxDynSmem)) {
         // horizontal scale <= 1: two adjacent columns per thread share their middle texel
         const long long tiles64 = (long long) ((a.ow + 63) / 64) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;

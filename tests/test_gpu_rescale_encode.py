@@ -87,7 +87,10 @@ def test_decode_rescale_policy():
         C.decode_rescale_nv12(1, ty, tc, None, out2, w=w, h=h)
     assert e.value.status == -7
     scratch = torch.zeros((1, h, w, 4), dtype=torch.uint8, device="cuda")
+    n0 = C.launch_count
     C.decode_rescale_nv12(1, ty, tc, scratch, out2, w=w, h=h, wait=True)
+    # 320 is not a multiple of 128: two kernels through the same-size intermediate, which `scratch` then holds
+    assert C.launch_count == n0 + 2
     _exact(scratch[0].cpu().numpy(), mid_want, "intermediate")
     _exact(out2[0].cpu().numpy(), ORA.rescale_bgra(mid_want, ow, oh), "two pass")
 

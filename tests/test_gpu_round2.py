@@ -381,3 +381,84 @@ def test_rescale_1080p_to_1440p_opaque_full_size():
     out = torch.zeros((1, 1440, 2560, 4), dtype=torch.uint8, device="cuda")
     ctx().rescale_bgra(dev(src)[None], out, wait=True)
     assert np.array_equal(out[0].cpu().numpy(), ORA.rescale_bgra(src, 2560, 1440))
+
+
+# ------------------------------------------------------------------ N1: fused decode -> rescale
+FUSED_CASES = [
+    # w, h, ow, oh, frames, gamma
+    (1920, 1080, 2560, 1440, 2, 3),   # BASELINE configs[1]
+    (1920, 1080, 2560, 1440, 1, 2),   # Linear mode: the decode reads the encode LUT; one frame (fewer slices than SMs)
+    (1280, 720, 1920, 1080, 3, 0),
+    (640, 360, 640, 481, 2, 1),       # same width, vertical upscale only
+    (256, 64, 258, 40, 4, 3),         # vertical downscale (1.6 source rows per output row)
+    (128, 2, 300, 7, 3, 1),           # a single row pair
+    (384, 130, 1000, 333, 2, 0),
+    (1920, 1080, 3840, 2160, 1, 3),
+]
+
+
+@pytest.mark.parametrize("w,h,ow,oh,F,gamma", FUSED_CASES)
+def test_fused_decode_rescale_equals_decode_then_rescale(w, h, ow, oh, F, gamma):
+    """bt709_decode_rescale_nv12 as ONE kernel: bit-identical to the oracle's decode followed by the
+    oracle's rescale, one launch, and the intermediate image is not in `scratch` afterwards"""
+    from _gpu import ctx, dev
+    frames = [frame_random(w, h, seed=1300 + f, full_range=(f % 2 == 1)) for f in range(F)]
+    ty = torch.stack([dev(y) for y, _ in frames])
+    tc = torch.stack([dev(c) for _, c in frames])
+    scratch = torch.zeros((F, h, w, 4), dtype=torch.uint8, device="cuda")
+    out = torch.zeros((F, oh, ow, 4), dtype=torch.uint8, device="cuda")
+    C = ctx()
+    n0 = C.launch_count
+    C.decode_rescale_nv12(gamma, ty, tc, scratch, out, wait=True)
+    assert C.launch_count == n0 + 1, "expected the fused kernel (one launch)"
+    got = out.cpu().numpy()
+    for f in range(F):
+        mid = ORA.decode_nv12(gamma, frames[f][0], frames[f][1])
+        want = ORA.rescale_bgra(mid, ow, oh)
+        assert np.array_equal(got[f], want), f"frame {f}: {(got[f] != want).sum()} byte mismatches"
+
+
+def test_fused_falls_back_to_two_passes():
+    """alpha stream, ragged width, padded scratch rows or BT709_NO_FUSED: two kernels, same result"""
+    from _gpu import ctx, dev
+    C = ctx()
+    w, h, ow, oh = 256, 64, 400, 100
+    y, c = frame_random(w, h, seed=5)
+    a, _ = frame_random(w, h, seed=6, full_range=True)
+    ty, tc, ta = dev(y)[None], dev(c)[None], dev(a)[None]
+    out = torch.zeros((1, oh, ow, 4), dtype=torch.uint8, device="cuda")
+    scratch = torch.zeros((1, h, w, 4), dtype=torch.uint8, device="cuda")
+    n0 = C.launch_count
+    C.decode_rescale_nv12(1, ty, tc, scratch, out, alpha_y=ta, wait=True)
+    assert C.launch_count == n0 + 2
+    mid = ORA.decode_nv12(1, y, c, alpha_y=a)
+    assert np.array_equal(scratch[0].cpu().numpy(), mid)
+    assert np.array_equal(out[0].cpu().numpy(), ORA.rescale_bgra(mid, ow, oh))
+    padded = torch.zeros((1, h, w + 8, 4), dtype=torch.uint8, device="cuda")[:, :, :w]
+    n0 = C.launch_count
+    C.decode_rescale_nv12(3, ty, tc, padded, out, wait=True)
+    assert C.launch_count == n0 + 2
+    mid = ORA.decode_nv12(3, y, c)
+    assert np.array_equal(out[0].cpu().numpy(), ORA.rescale_bgra(mid, ow, oh))
+
+
+def test_fused_full_batch_checksum_against_two_passes():
+    """a 1080p -> 1440p batch larger than the number of SMs x bands per slice: the fused kernel against the two
+    separate C-ABI calls on the same inputs (every byte)"""
+    from _gpu import ctx
+    C = ctx()
+    F, w, h, ow, oh = 40, 1920, 1080, 2560, 1440
+    g = torch.Generator(device="cuda")
+    g.manual_seed(99)
+    ty = torch.randint(16, 236, (F, h, w), dtype=torch.uint8, device="cuda", generator=g)
+    tc = torch.randint(16, 241, (F, h // 2, w), dtype=torch.uint8, device="cuda", generator=g)
+    mid = torch.empty((F, h, w, 4), dtype=torch.uint8, device="cuda")
+    want = torch.empty((F, oh, ow, 4), dtype=torch.uint8, device="cuda")
+    C.decode_nv12(3, ty, tc, mid)
+    C.rescale_bgra(mid, want, wait=True)
+    got = torch.zeros_like(want)
+    scratch = torch.empty((F, h, w, 4), dtype=torch.uint8, device="cuda")
+    n0 = C.launch_count
+    C.decode_rescale_nv12(3, ty, tc, scratch, got, wait=True)
+    assert C.launch_count == n0 + 1
+    assert torch.equal(got, want)
