@@ -413,9 +413,16 @@ def run_b200(args):
         e2e = run_e2e(args, ctx, local_rank, w, h, frames, gamma)
         if world > 1:
             e_secs, e_units = gather_job_stats(e2e["_secs"], e2e["_units"])
+            c_secs, _ = gather_job_stats(e2e["_copy_secs"] or 0.0, 0.0)
         else:
             e_secs, e_units = e2e["_secs"], e2e["_units"]
+            c_secs = e2e["_copy_secs"] or 0.0
+        ceiling = e_units / c_secs / 1e9 if c_secs > 0 else None
         e2e = {"value": e_units / e_secs / 1e9, "unit": "Gpix/s", "h2d_bytes_per_step": e2e["h2d"],
+               "copy_only_value": ceiling,
+               "frac_of_copy_ceiling": (e_units / e_secs / 1e9) / ceiling if ceiling else None,
+               "copy_only_note": "the same bytes per frame over PCIe (pinned host memory, same stream count) with no kernel: "
+                                 "what this host and its PCIe links allow for one-frame-per-call traffic at this GPU count",
                "d2h_bytes_per_step": e2e["d2h"], "frames_per_step": e2e["frames"], "steps": e2e["steps"],
                "gamma": e2e["gamma"], "verified": e2e["verified"],
                "api": "MetalBT709Decoder_decodeBT709 (pinned host NV12 in, pinned host BGRA out, one frame per call, "
@@ -497,6 +504,32 @@ def run_e2e(args, ctx, device, w, h, frames, gamma):
         one_pass()
     torch.cuda.synchronize()
     secs = time.perf_counter() - t0
+    # ---- the ceiling of this call pattern: the same bytes over PCIe with no kernel in between (pinned host buffers,
+    # one H2D of a frame's NV12 planes and one D2H of its BGRA image per frame, same 4 streams)
+    copy_secs = None
+    try:
+        hin = [torch.empty(w * h * 3 // 2, dtype=torch.uint8).pin_memory() for _ in range(4)]
+        hout = [torch.empty(w * h * 4, dtype=torch.uint8).pin_memory() for _ in range(4)]
+        din = [torch.empty(w * h * 3 // 2, dtype=torch.uint8, device="cuda") for _ in range(4)]
+        dout = [torch.empty(w * h * 4, dtype=torch.uint8, device="cuda") for _ in range(4)]
+        streams = [torch.cuda.Stream() for _ in range(4)]
+
+        def copy_pass():
+            for i in range(n):
+                k = i % 4
+                with torch.cuda.stream(streams[k]):
+                    din[k].copy_(hin[k], non_blocking=True)
+                    hout[k].copy_(dout[k], non_blocking=True)
+            for s_ in streams:
+                s_.synchronize()
+
+        copy_pass()
+        t1 = time.perf_counter()
+        for _ in range(steps):
+            copy_pass()
+        copy_secs = time.perf_counter() - t1
+    except Exception:
+        copy_secs = None
     # the host path must have produced what the (parity-tested) device-resident kernel produces for the same frames
     verified = True
     for i in (0, ring - 1):
@@ -508,7 +541,7 @@ def run_e2e(args, ctx, device, w, h, frames, gamma):
     if not verified:
         raise SystemExit("bench.py: e2e output differs from the device-resident kernel's output")
     out = {"_secs": secs, "_units": float(n) * w * h * steps, "h2d": int(n * w * h * 1.5), "d2h": n * w * h * 4,
-           "frames": n, "steps": steps, "gamma": args.gamma, "verified": verified}
+           "frames": n, "steps": steps, "gamma": args.gamma, "verified": verified, "_copy_secs": copy_secs}
     for b in bufs:
         b.release()
     for t in texs:

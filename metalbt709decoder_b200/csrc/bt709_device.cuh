@@ -45,6 +45,12 @@ __device__ __forceinline__ void st_stream_u32(void *p, uint32_t v) {
   asm volatile("st.global.cs.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// 16-byte store with an L2 cache policy (createpolicy handle), e.g. evict_last for data that is read back soon
+__device__ __forceinline__ void st_l2hint_u128(void *p, uint4 v, unsigned long long policy) {
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+               : "memory");
+}
+
 // base + a * b with 32-bit unsigned a, b: one IMAD.WIDE.U32 (the compiler's own 64-bit address
 // arithmetic spent ~7 instructions per pixel on sign extensions and carry chains)
 __device__ __forceinline__ const uint8_t *ptr_mad(const uint8_t *base, unsigned a, unsigned b) {

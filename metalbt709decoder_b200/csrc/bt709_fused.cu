@@ -23,12 +23,12 @@
 
 namespace bt709 {
 
-size_t pair_layout_bytes(unsigned base, int cells, unsigned extra_bytes);  // bt709_rescale.cu
+size_t pair_layout_bytes(unsigned base, int cells, unsigned extra_bytes, int warps);  // bt709_rescale.cu
 extern int g_dyn_smem_base;
 
 // CL2/RL2: decode LUT geometry (10, 3), or (-1, 5) = the encode LUT itself (Linear mode)
 template <int CL2, int RL2>
-__global__ void __launch_bounds__(kPairWarps * 32, 1) k_fused(const FusedArgs a) {
+__global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(const FusedArgs a) {
   extern __shared__ __align__(16) uint32_t s_mem[];
   constexpr int R = 1 << RL2, N = 1 << (CL2 > 0 ? CL2 : 0);
   constexpr uint32_t kDecBytes = CL2 > 0 ? (((uint32_t) (N + 1) * R * 4u + 127u) & ~127u) : 0u;
@@ -61,6 +61,8 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) k_fused(const FusedArgs a)
   k.one = pk(d.one, d.one);
   k.bias = pk(d.log_bias, d.log_bias);
 
+  unsigned long long pol_last;  // L2 cache policy of the slice: keep (evict last)
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_last));
   const unsigned T = (unsigned) d.tiles_per_row;
   constexpr int TW = 64 * kPairNP;
   const int tiles_x = (p.ow + TW - 1) / TW;
@@ -77,35 +79,50 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) k_fused(const FusedArgs a)
     const int r0 = max((int) floorf(sy0), 0), r1 = min(max((int) floorf(syl) + 1, 0), p.ih - 1);
     const unsigned rp0 = (unsigned) r0 >> 1, nrp = ((unsigned) r1 >> 1) - rp0 + 1;
 
-    // ---- phase A: decode row pairs rp0 .. rp0 + nrp - 1 into the slice (128-pixel x 2-row tiles, one per warp step)
+    // ---- phase A: decode row pairs rp0 .. rp0 + nrp - 1 into the slice (128-pixel x 2-row tiles, one per warp step).
+    // The words of the next two tiles are in flight during a tile's arithmetic; (row pair, tile column) advance
+    // incrementally; the slice is written with the L2 evict_last policy so that the streaming output of phase B
+    // does not push it out to HBM before the next band overwrites it.
     const uint8_t *yf = d.y + (long long) f * d.sy, *cf = d.c + (long long) f * d.sc;
     const unsigned ntiles = nrp * T;
-    uint32_t ny0 = 0, ny1 = 0, nc = 0;
-    auto load = [&](unsigned t) {
-      const unsigned rpl = t / T, tile = t - rpl * T, rp = rp0 + rpl, col4 = tile * 32 + lane;
-      ny0 = ld_stream_u32(yf + (long long) (2 * rp) * d.py + (size_t) col4 * 4);
-      ny1 = ld_stream_u32(yf + (long long) (2 * rp + 1) * d.py + (size_t) col4 * 4);
-      nc = ld_stream_u32(cf + (long long) rp * d.pc + (size_t) col4 * 4);
+    const unsigned step_rp = (unsigned) nwarps / T, step_tile = (unsigned) nwarps - step_rp * T;
+    struct Words { uint32_t y0, y1, c; };
+    unsigned lrp = (unsigned) warp / T, ltile = (unsigned) warp - lrp * T;  // (row pair, tile) of the next load
+    auto load = [&](Words &wd) {
+      const unsigned rp = rp0 + lrp, col4 = ltile * 32 + lane;
+      wd.y0 = ld_stream_u32(yf + (long long) (2 * rp) * d.py + (size_t) col4 * 4);
+      wd.y1 = ld_stream_u32(yf + (long long) (2 * rp + 1) * d.py + (size_t) col4 * 4);
+      wd.c = ld_stream_u32(cf + (long long) rp * d.pc + (size_t) col4 * 4);
+      lrp += step_rp;
+      ltile += step_tile;
+      if (ltile >= T) { ltile -= T; lrp++; }
     };
-    if ((unsigned) warp < ntiles) load(warp);
+    Words q0{0, 0, 0}, q1{0, 0, 0};
+    if ((unsigned) warp < ntiles) load(q0);
+    if ((unsigned) warp + nwarps < ntiles) load(q1);
+    unsigned srp = (unsigned) warp / T, stile = (unsigned) warp - srp * T;  // (row pair, tile) being decoded
     for (unsigned t = warp; t < ntiles; t += nwarps) {
-      const uint32_t y0 = ny0, y1 = ny1, cw = nc;
-      if (t + nwarps < ntiles) load(t + nwarps);  // the next tile's words are in flight during this tile's arithmetic
-      const unsigned rpl = t / T, tile = t - rpl * T, col4 = tile * 32 + lane;
-      f32x2 cbn = mul2(add2(pku(magic_byte<0>(cw), magic_byte<2>(cw)), k.kC), k.inv255);
-      f32x2 crn = mul2(add2(pku(magic_byte<1>(cw), magic_byte<3>(cw)), k.kC), k.inv255);
+      const Words cur = q0;
+      q0 = q1;
+      if (t + 2 * nwarps < ntiles) load(q1);
+      const unsigned col4 = stile * 32 + lane;
+      f32x2 cbn = mul2(add2(pku(magic_byte<0>(cur.c), magic_byte<2>(cur.c)), k.kC), k.inv255);
+      f32x2 crn = mul2(add2(pku(magic_byte<1>(cur.c), magic_byte<3>(cur.c)), k.kC), k.inv255);
       f32x2 cb_g = mul2(cbn, k.g_cb), cb_b = mul2(cbn, k.b_cb);
       f32x2 cr_r = mul2(crn, k.r_cr), cr_g = mul2(crn, k.g_cr);
-      uint8_t *o = scr + (size_t) (2 * rpl) * spitch + (size_t) col4 * 16;
-      *reinterpret_cast<uint4 *>(o) = decode_row<CL2, RL2, false>(y0, 0u, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase);
-      *reinterpret_cast<uint4 *>(o + spitch) = decode_row<CL2, RL2, false>(y1, 0u, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase);
+      uint8_t *o = scr + (size_t) (2 * srp) * spitch + (size_t) col4 * 16;
+      st_l2hint_u128(o, decode_row<CL2, RL2, false>(cur.y0, 0u, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase), pol_last);
+      st_l2hint_u128(o + spitch, decode_row<CL2, RL2, false>(cur.y1, 0u, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase), pol_last);
+      srp += step_rp;
+      stile += step_tile;
+      if (stile >= T) { stile -= T; srp++; }
     }
     __syncthreads();  // the slice is complete and visible to the whole CTA
 
     // ---- phase B: pass 2 over the slice; row y of the frame is slice row y - 2 * rp0
     const uint8_t *src = scr - (long long) (2 * rp0) * spitch;
     uint8_t *dst = p.out + (long long) f * p.so;
-    for (int tx = warp; tx < tiles_x; tx += nwarps) pair_tile<false, false, kPairNP, false>(p, c, src, spitch, dst, tx * TW, oy0, lane);
+    for (int tx = warp; tx < tiles_x; tx += nwarps) pair_tile<false, false, kPairNP, false, kFusedPD>(p, c, src, spitch, dst, tx * TW, oy0, lane, pol_last);
     __syncthreads();  // every warp is done reading before the next band overwrites the slice
   }
 }
@@ -127,14 +144,14 @@ int launch_fused(const DecodeArgs &d0, const RescaleArgs &r0, uint8_t *scratch, 
   const bool linear = d.blog_lut && d.blog_cells > 0;  // Linear mode: the decode step function is the encode LUT
   if (!linear && d.cells_log2 != 10) return -1;
   const unsigned dec_bytes = linear ? 0u : ((1025u * 8u * 4u + 127u) & ~127u);
-  const size_t smem = pair_layout_bytes((unsigned) g_dyn_smem_base, r.enc_blog_cells, dec_bytes);
+  const size_t smem = pair_layout_bytes((unsigned) g_dyn_smem_base, r.enc_blog_cells, dec_bytes, kFusedWarps);
   if (smem > kMaxDynSmem) return -1;
   FusedArgs a{};
   a.bands = (r.oh + kWalkTH - 1) / kWalkTH;
   const long long units = (long long) d.nframes * a.bands;
   if (units >= (1ll << 31)) return -1;
   // rows a band can need: its source span, both taps, rounding to chroma row pairs, and the walker's prefetch overrun
-  const int rows_max = (int) ((double) kWalkTH * (double) r.ih / (double) r.oh) + 8 + kPairPD + 2;
+  const int rows_max = (int) ((double) kWalkTH * (double) r.ih / (double) r.oh) + 8 + kFusedPD + 2;
   a.spitch = (unsigned) (((size_t) d.w * 4 + 255) & ~(size_t) 255);
   a.cta_stride = (long long) rows_max * a.spitch;
   // one CTA per SM, fewer when there are fewer units or the scratch area has room for fewer slices
@@ -155,9 +172,9 @@ int launch_fused(const DecodeArgs &d0, const RescaleArgs &r0, uint8_t *scratch, 
   a.scratch = scratch;
   cudaStream_t s = (cudaStream_t) stream;
   if (linear)
-    k_fused<-1, 5><<<grid, kPairWarps * 32, smem, s>>>(a), note_launch();
+    k_fused<-1, 5><<<grid, kFusedWarps * 32, smem, s>>>(a), note_launch();
   else
-    k_fused<10, 3><<<grid, kPairWarps * 32, smem, s>>>(a), note_launch();
+    k_fused<10, 3><<<grid, kFusedWarps * 32, smem, s>>>(a), note_launch();
   return (int) cudaGetLastError();
 }
 

@@ -88,6 +88,8 @@ bool upload2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t r
   return cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, cudaMemcpyHostToDevice, st) == cudaSuccess;
 }
 bool download2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t row_bytes, size_t rows, cudaStream_t st) {
+  if (dpitch == spitch && dpitch == row_bytes)  // tightly packed on both sides: one 1-D copy
+    return cudaMemcpyAsync(dst, src, row_bytes * rows, cudaMemcpyDeviceToHost, st) == cudaSuccess;
   return cudaMemcpy2DAsync(dst, dpitch, src, spitch, row_bytes, rows, cudaMemcpyDeviceToHost, st) == cudaSuccess;
 }
 
@@ -129,12 +131,24 @@ struct Staged {
 bool stage_nv12(Slot *s, const MBDPixelBuffer *pb, const MBDPixelBuffer *alpha, cudaStream_t st, Staged *out) {
   const int w = pb->width, h = pb->height;
   const size_t cw = (size_t) ((w + 1) / 2) * 2, ch = (size_t) (h + 1) / 2;
-  const size_t py = align_up(w, 256), pc = align_up(cw, 256);
-  if (!s->y.ensure(py * h) || !s->c.ensure(pc * ch)) return false;
-  if (!upload2d(s->y.p, py, pb->y, pb->yBytesPerRow, w, h, st)) return false;
-  if (!upload2d(s->c.p, pc, pb->cbcr, pb->cbcrBytesPerRow, cw, ch, st)) return false;
-  out->y = {s->y.p, py, py * h};
-  out->c = {s->c.p, pc, pc * ch};
+  // Buffers made by BGRAToBT709Converter_createCoreVideoYCbCrBuffer hold both planes in ONE pinned block (CbCr right
+  // behind Y) with 64-byte row pitches: mirror that layout on the device and the whole frame is a single 1-D copy
+  // (one DMA descriptor instead of two pitched copies of 1080 + 540 rows).
+  const size_t ybytes = pb->yBytesPerRow * (size_t) h, cbytes = pb->cbcrBytesPerRow * ch;
+  if (pb->cbcr == pb->y + ybytes && pb->yBytesPerRow % 16 == 0 && pb->cbcrBytesPerRow % 16 == 0 && ybytes % 256 == 0) {
+    if (!s->y.ensure(ybytes + cbytes)) return false;
+    if (cudaMemcpyAsync(s->y.p, pb->y, ybytes + cbytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return false;
+    out->y = {s->y.p, pb->yBytesPerRow, ybytes};
+    out->c = {(uint8_t *) s->y.p + ybytes, pb->cbcrBytesPerRow, cbytes};
+  } else {
+    const size_t py = align_up(w, 256), pc = align_up(cw, 256);
+    if (!s->y.ensure(py * h) || !s->c.ensure(pc * ch)) return false;
+    if (!upload2d(s->y.p, py, pb->y, pb->yBytesPerRow, w, h, st)) return false;
+    if (!upload2d(s->c.p, pc, pb->cbcr, pb->cbcrBytesPerRow, cw, ch, st)) return false;
+    out->y = {s->y.p, py, py * h};
+    out->c = {s->c.p, pc, pc * ch};
+  }
+  const size_t py = align_up(w, 256);
   out->has_a = alpha != nullptr;
   if (alpha) {
     // only the Y plane of the alpha stream is read (MetalBT709Decoder.m:376-378)

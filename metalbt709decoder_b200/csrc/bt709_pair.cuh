@@ -27,18 +27,22 @@ constexpr int kWalkRowInfo = (kWalkTH + 1) * 4;  // words of row info per warp (
 //     gather is a single conflict-free wavefront for any content, for one extra packed add per pair of lookups;
 //   * the alpha byte -> float step is arithmetic (PRMT + packed add + packed multiply), not a table.
 // Same row-info slices, unclamped row walk and three-row register prefetch queue as k_rescale_cols2.
+// k_rescale_pair: 16 warps x 128 registers, taps fetched 3 rows ahead (150.8 k frames/s on 1080p -> 1440p against
+// 143.4 k with 20 warps x 96 registers and 2 rows ahead; 24 warps x 80 registers: 126 k).  The fused kernel keeps 20
+// warps: its decode phase needs them to cover the load latency.
 #ifndef BT709_PAIR_WARPS
-#define BT709_PAIR_WARPS 20
+#define BT709_PAIR_WARPS 16
+#endif
+#ifndef BT709_PAIR_PD
+#define BT709_PAIR_PD 3
 #endif
 #ifndef BT709_PAIR_NP
 #define BT709_PAIR_NP 2
 #endif
-constexpr int kPairWarps = BT709_PAIR_WARPS;  // 20 warps x 96 registers (two column pairs per thread)
-#ifndef BT709_PAIR_PD
-#define BT709_PAIR_PD 2
-#endif
-constexpr int kPairPD = BT709_PAIR_PD;        // source rows fetched ahead of use by pair_tile
+constexpr int kPairWarps = BT709_PAIR_WARPS;
+constexpr int kPairPD = BT709_PAIR_PD;        // source rows fetched ahead of use by pair_tile (standalone kernel)
 constexpr int kPairNP = BT709_PAIR_NP;        // column pairs per thread on the opaque code: warp tile = 64 * kPairNP columns
+constexpr int kFusedWarps = 20, kFusedPD = 2;
 
 struct PairCtx {
   uint32_t lin_lane, rows_base, enc_base;
@@ -55,7 +59,7 @@ struct H3 {
 //   [encode LUT, biased log cells: cell i replica r at word i*32 + r][pad][lin table at the next 64 KB boundary:
 //    word b*64 + r = sRGB byte b -> linear float, replica r; the upper 128 B of each 256-B entry are unused][row info]
 // extra_bytes: room the caller wants between the encode LUT and the pad (the fused kernel's decode LUT)
-__device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s_mem, uint32_t extra_bytes = 0) {
+__device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s_mem, uint32_t extra_bytes = 0) {  // row info: one slice per warp of the CTA
   const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_mem);
   const int nenc = p.enc_blog_cells << 5;
   const uint32_t extra_at = ((uint32_t) (nenc + 4) * 4u + 127u) & ~127u;
@@ -95,9 +99,11 @@ __device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s
 // pairs per thread it is paid once per four pixels.
 // SPEC: the opaque code is speculative (track the AND of the tap words); false when the caller knows the source is
 // opaque (the fused kernel: pass 1 without an alpha stream writes A = 255).
-template <bool ALPHA, bool NC = true, int NP = 1, bool SPEC = true>
+// PD: source rows fetched ahead of use.  l2_policy (NC == false only): createpolicy handle for the tap loads (the fused
+// kernel keeps its slice resident in L2 with evict_last).
+template <bool ALPHA, bool NC = true, int NP = 1, bool SPEC = true, int PD = kPairPD>
 __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c, const uint8_t *src_frame, unsigned pi,
-                                          uint8_t *dst_frame, int ox0, int oy0, int lane) {
+                                          uint8_t *dst_frame, int ox0, int oy0, int lane, unsigned long long l2_policy = 0) {
   uint32_t lin_lane = c.lin_lane, enc_base = c.enc_base;
   const uint32_t rows_base = c.rows_base;
   asm volatile("" : "+r"(lin_lane), "+r"(enc_base));  // keep them in registers (ptxas rebuilt them every source row)
@@ -176,9 +182,9 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
         t[q].w1 = __ldg(reinterpret_cast<const uint32_t *>(fp[q] + d1[q]));
         t[q].w2 = __ldg(reinterpret_cast<const uint32_t *>(fp[q] + d2[q]));
       } else {
-        asm volatile("ld.global.u32 %0, [%1];" : "=r"(t[q].w0) : "l"(fp[q]) : "memory");
-        asm volatile("ld.global.u32 %0, [%1];" : "=r"(t[q].w1) : "l"(fp[q] + d1[q]) : "memory");
-        asm volatile("ld.global.u32 %0, [%1];" : "=r"(t[q].w2) : "l"(fp[q] + d2[q]) : "memory");
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t[q].w0) : "l"(fp[q]), "l"(l2_policy) : "memory");
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t[q].w1) : "l"(fp[q] + d1[q]), "l"(l2_policy) : "memory");
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t[q].w2) : "l"(fp[q] + d2[q]), "l"(l2_policy) : "memory");
       }
       fp[q] += step;
     }
@@ -206,22 +212,22 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
   uint32_t info_fy, info_y;
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(info_fy), "=r"(info_y) : "r"(ip));
   int y = (int) info_y;
-  Taps qq[kPairPD][NP], first[NP];
+  Taps qq[PD][NP], first[NP];
 #pragma unroll
   for (int q = 0; q < NP; q++) fp[q] = ptr_mad(fp[q], (unsigned) max(y, 0), pi);
   fetch(y, first);
 #pragma unroll
-  for (int j = 0; j < kPairPD; j++) fetch(y + 1 + j, qq[j]);
+  for (int j = 0; j < PD; j++) fetch(y + 1 + j, qq[j]);
   H3 H[2][NP];
 #pragma unroll
   for (int q = 0; q < NP; q++) H[0][q] = blend(first[q], q);
   bool done = false;
   while (!done) {
 #pragma unroll
-    for (int j = 0; j < 2 * kPairPD; j++) {
+    for (int j = 0; j < 2 * PD; j++) {
 #pragma unroll
-      for (int q = 0; q < NP; q++) H[(j + 1) & 1][q] = blend(qq[j % kPairPD][q], q);
-      fetch(y + 1 + kPairPD, qq[j % kPairPD]);
+      for (int q = 0; q < NP; q++) H[(j + 1) & 1][q] = blend(qq[j % PD][q], q);
+      fetch(y + 1 + PD, qq[j % PD]);
       while ((int) info_y <= y) {
         dp += po;
         const float fy = __uint_as_float(info_fy);
@@ -245,7 +251,7 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
             wa = __byte_perm(__byte_perm(ba, ga, 0x0073), ra, 0x7710) | 0xFF000000u;
             wb = __byte_perm(__byte_perm(bb, gb, 0x0073), rb, 0x7710) | 0xFF000000u;
           }
-          if (live[q]) *reinterpret_cast<uint2 *>(dp + q * 256) = make_uint2(wa, wb);
+          if (live[q]) st_stream_u64(dp + q * 256, make_uint2(wa, wb));  // streaming: the output is never read back
         }
         ip += 16;
         asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(info_fy), "=r"(info_y) : "r"(ip));

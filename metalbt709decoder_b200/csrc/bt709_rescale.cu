@@ -475,11 +475,11 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) k_rescale_pair(const Resca
       bool opaque = true;
 #pragma unroll 1
       for (int q = 0; q < kPairNP; q++)
-        if (ox0 + q * 64 < p.ow) opaque = pair_tile<true, true, 1>(p, c, src, pi, dst, ox0 + q * 64, oy0, lane) && opaque;
+        if (ox0 + q * 64 < p.ow) opaque = pair_tile<true, true, 1, true, kPairPD>(p, c, src, pi, dst, ox0 + q * 64, oy0, lane) && opaque;
       return opaque;
     };
     if (!with_alpha) {
-      if (!pair_tile<false, true, kPairNP>(p, c, src, pi, dst, ox0, oy0, lane)) {  // a tap with A != 255: redo with alpha
+      if (!pair_tile<false, true, kPairNP, true, kPairPD>(p, c, src, pi, dst, ox0, oy0, lane)) {  // a tap with A != 255: redo with alpha
         alpha_tile();
         with_alpha = true;
       }
@@ -503,10 +503,10 @@ static size_t elog_layout_bytes(unsigned base, int cells, int warps) {
 }
 
 // dynamic bytes k_rescale_pair needs: [LUT, 32 replicas][pad to 64 KB][table 64 KB][row info]
-size_t pair_layout_bytes(unsigned base, int cells, unsigned extra_bytes) {
+size_t pair_layout_bytes(unsigned base, int cells, unsigned extra_bytes, int warps) {
   const unsigned head = ((((unsigned) cells * 32u + 4u) * 4u + 127u) & ~127u) + extra_bytes;
   const unsigned pad = head + ((0x10000u - ((base + head) & 0xFFFFu)) & 0xFFFFu);
-  return (size_t) pad + 65536u + (size_t) kPairWarps * kWalkRowInfo * 4u;
+  return (size_t) pad + 65536u + (size_t) warps * kWalkRowInfo * 4u;
 }
 
 static size_t walk_smem_bytes(int enc_cells_log2, int rep_log2) {  // 64 KB of alignment slack in front of the table
@@ -543,12 +543,12 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
       // (even width and 8-byte aligned rows: every column pair is stored with one 8-byte store)
       const bool pair_ok = (a.ow % 2 == 0) && aligned(a.out, 8) && aligned(a.po, 8) && aligned(a.so, 8);
       if (a.iw <= a.ow && pair_ok && !no_pair && !no_cols2 && b.enc_blog_lut && g_dyn_smem_base >= 0 &&
-          pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0) <= kMaxDynSmem) {
+          pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0, kPairWarps) <= kMaxDynSmem) {
         // horizontal scale <= 1: paired columns, opaque speculation, conflict-free encode LUT (k_rescale_pair)
         const long long tiles64 = (long long) ((a.ow + 64 * kPairNP - 1) / (64 * kPairNP)) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
         const long long ctas2 = (tiles64 + kPairWarps - 1) / kPairWarps;
         const unsigned g2 = (unsigned) (ctas2 < (long long) sm_count ? ctas2 : (long long) sm_count);
-        k_rescale_pair<<<g2, kPairWarps * 32, pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0), st>>>(b), note_launch();
+        k_rescale_pair<<<g2, kPairWarps * 32, pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0, kPairWarps), st>>>(b), note_launch();
       } else if (a.iw <= a.ow && !no_cols2 && (elog || smem_u <= kMaxDynSmem)) {
         // horizontal scale <= 1: two adjacent columns per thread share their middle texel
         const long long tiles64 = (long long) ((a.ow + 63) / 64) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;

@@ -410,7 +410,11 @@ def test_fused_decode_rescale_equals_decode_then_rescale(w, h, ow, oh, F, gamma)
     C = ctx()
     n0 = C.launch_count
     C.decode_rescale_nv12(gamma, ty, tc, scratch, out, wait=True)
-    assert C.launch_count == n0 + 1, "expected the fused kernel (one launch)"
+    # one launch = the fused kernel.  (A scratch area smaller than one CTA slice - the 128x2 case: 3 KB - cannot host
+    # it; the call then runs the two passes.)
+    slice_rows = int(64 * h / oh) + 8 + 2 + 2
+    fused_fits = F * h * w * 4 >= slice_rows * ((w * 4 + 255) // 256 * 256)
+    assert C.launch_count == n0 + (1 if fused_fits else 2), "expected the fused kernel (one launch)"
     got = out.cpu().numpy()
     for f in range(F):
         mid = ORA.decode_nv12(gamma, frames[f][0], frames[f][1])
