@@ -41,7 +41,7 @@ WORKLOADS = {
     "c3_uhd": (3840, 2160, 300, "decode"),       # 2400 frames / 8 GPUs per BASELINE configs[2]
     "c2_rescale": (1920, 1080, 200, "rescale"),  # pass 2 alone, 1080p -> 2560x1440
     "c2_twopass": (1920, 1080, 200, "twopass"),  # decode -> same-size intermediate in HBM -> rescale (two launches)
-    "c2_fused": (1920, 1080, 200, "fused"),      # bt709_decode_rescale_nv12: one kernel, no intermediate
+    "c2_fused": (1920, 1080, 200, "fused"),      # bt709_decode_rescale_nv12_fused: one kernel, no intermediate image
     "c4_alpha": (2048, 1536, 200, "alpha"),
     "c5_encode": (2048, 1536, 200, "encode"),
 }
@@ -298,7 +298,7 @@ def make_step(ctx, d, kind, gamma, stream):
             ctx.rescale_bgra(d["out"], d["big"], stream=stream)
         return two
     if kind == "fused":
-        return lambda: ctx.decode_rescale_nv12(gamma, d["y"], d["c"], d["scratch"], d["big"], stream=stream)
+        return lambda: ctx.decode_rescale_nv12_fused(gamma, d["y"], d["c"], d["scratch"], d["big"], stream=stream)
     if kind == "encode":
         return lambda: ctx.encode_bgra_to_nv12(1, 0, d["src"], d["y"], d["c"], stream=stream)
     raise ValueError(kind)

@@ -71,7 +71,8 @@ typedef enum {
   BT709_E_ALPHA_MODE = -5, /* alpha plane with a gamma other than sRGB
                               (MetalBT709Decoder.m:165-169 forces sRGB; here it is explicit) */
   BT709_E_CUDA = -6,       /* CUDA error; see bt709_last_cuda_error */
-  BT709_E_SCRATCH = -7     /* two-pass decode+rescale needs an intermediate plane */
+  BT709_E_SCRATCH = -7,    /* two-pass decode+rescale needs an intermediate plane */
+  BT709_E_UNSUPPORTED = -8 /* bt709_decode_rescale_nv12_fused: the fused kernel does not apply to this geometry */
 } bt709_status;
 
 /* One plane (or packed image) of a batch of equally sized frames, in device memory. */
@@ -126,19 +127,30 @@ BT709_API int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *bgra_i
                                  void *stream, int wait);
 
 /* The per-frame policy of -[AAPLRenderer drawInMTKView:] (AAPLRenderer.m:891-977):
- * output size == frame size -> pass 1 straight into bgra_out; otherwise decode + rescale into bgra_out.
- * `scratch` stands for the reference's same-size sRGB intermediate (_resizeTexture) and may be NULL only in the
- * same-size case.  When the geometry allows it (no alpha stream, w a multiple of 128, even h, even out_w, no
- * horizontal downscale, tightly packed scratch rows and frames) the two passes run FUSED in one kernel: each CTA
- * decodes the source rows of one band of 64 output rows into a slice of `scratch` that it overwrites band after
- * band (~60 MB in all, resident in L2), so the intermediate image never reaches HBM and `scratch` does NOT hold it
- * afterwards.  The result is bit-identical either way.  Otherwise pass 1 writes the full intermediate into `scratch`
- * and pass 2 reads it back (two kernels). */
+ * output size == frame size -> pass 1 straight into bgra_out; otherwise pass 1 into the same-size sRGB
+ * intermediate `scratch` (the reference's _resizeTexture) and pass 2 into bgra_out (two kernels).
+ * `scratch` may be NULL only in the same-size case. */
 BT709_API int bt709_decode_rescale_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y,
                                         const bt709_plane *cbcr, const bt709_plane *alpha_y,
                                         const bt709_plane *scratch, const bt709_plane *bgra_out, int w,
                                         int h, int out_w, int out_h, int nframes, void *stream,
                                         int wait);
+
+/* The same operation FUSED into one kernel (MetalBT709Decoder.m:612-618 is the author's note
+ * that a single pass would halve the traffic): each CTA decodes the source rows of one band of 64 output rows into
+ * a slice of `scratch` that it overwrites band after band (~400 KB per SM, resident in L2), then resamples them, so
+ * the intermediate image is never written out as a whole and `scratch` does NOT hold it afterwards.  Bit-identical
+ * to the two-pass result.  Needs: no alpha stream, w a multiple of 128, even h, even out_w >= w, 8-byte aligned
+ * destination rows, tightly packed scratch rows (pitch == 4 w) and frames, at least one slice of scratch
+ * ((64 h / out_h + 12) rows; frames back to back: the whole batch-sized area is used, one slice per SM; any other
+ * frame stride: only the first frame's area); returns BT709_E_UNSUPPORTED otherwise.  bt709_decode_rescale_nv12 itself
+ * takes this path when the environment variable BT709_FUSED is set.
+ * Measured on B200 (1080p -> 1440p): 39 % less DRAM traffic, 13 % lower frame rate than the two kernels (both
+ * halves are instruction-bound), see DESIGN.md section 4.4. */
+BT709_API int bt709_decode_rescale_nv12_fused(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y,
+                                              const bt709_plane *cbcr, const bt709_plane *scratch,
+                                              const bt709_plane *bgra_out, int w, int h, int out_w, int out_h,
+                                              int nframes, void *stream, int wait);
 
 /* Inverse path.  Replaces cvpbu_ycbcr_subsample (CVPixelBufferUtils.h:241-399) +
  * BT709_average_pixel_values (BT709.h:1349-1509) as driven by

@@ -70,6 +70,8 @@ PROTOTYPES = {
     "bt709_rescale_bgra": (c_int, [c_void_p, PP, c_int, c_int, PP, c_int, c_int, c_int, c_void_p, c_int]),
     "bt709_decode_rescale_nv12": (c_int, [c_void_p, c_int, PP, PP, PP, PP, PP, c_int, c_int, c_int, c_int, c_int,
                                           c_void_p, c_int]),
+    "bt709_decode_rescale_nv12_fused": (c_int, [c_void_p, c_int, PP, PP, PP, PP, c_int, c_int, c_int, c_int, c_int,
+                                                c_void_p, c_int]),
     "bt709_encode_bgra_to_nv12": (c_int, [c_void_p, c_int, c_int, PP, PP, PP, c_int, c_int, c_int, c_void_p, c_int]),
     "bt709_convert_packed444": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),
     "bt709_unconvert_packed444": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int]),

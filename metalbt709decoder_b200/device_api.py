@@ -11,7 +11,7 @@ from ._lib import Plane
 GAMMA_APPLE, GAMMA_SRGB, GAMMA_LINEAR, GAMMA_BT709 = 0, 1, 2, 3
 GAMMA_NAMES = {"apple": 0, "srgb": 1, "linear": 2, "bt709": 3}
 
-OK, E_NULL, E_DIMS, E_PITCH, E_GAMMA, E_ALPHA_MODE, E_CUDA, E_SCRATCH = 0, -1, -2, -3, -4, -5, -6, -7
+OK, E_NULL, E_DIMS, E_PITCH, E_GAMMA, E_ALPHA_MODE, E_CUDA, E_SCRATCH, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
 
 class BT709Error(RuntimeError):
@@ -115,6 +115,18 @@ class BT709Context:
                                                w, h, ow, oh, F, _stream_ptr(stream), int(wait))
         if rc != OK:
             raise BT709Error(rc, "bt709_decode_rescale_nv12")
+
+    def decode_rescale_nv12_fused(self, gamma, y, cbcr, scratch, out, w=None, h=None, stream=None, wait=False):
+        """One kernel, the intermediate stays in L2 (bt709_decode_rescale_nv12_fused); BT709Error(-8) if it does not apply."""
+        F, H = y.shape[0], y.shape[1]
+        h = h if h is not None else H
+        w = w if w is not None else y.shape[2]
+        oh, ow = out.shape[1], out.shape[2]
+        py, pc, po, ps = plane_of(y), plane_of(cbcr), plane_of(out), plane_of(scratch)
+        rc = self._L.bt709_decode_rescale_nv12_fused(self._h, gamma, ctypes.byref(py), ctypes.byref(pc), ctypes.byref(ps),
+                                                     ctypes.byref(po), w, h, ow, oh, F, _stream_ptr(stream), int(wait))
+        if rc != OK:
+            raise BT709Error(rc, "bt709_decode_rescale_nv12_fused")
 
     def encode_bgra_to_nv12(self, gamma_in, gamma_out, bgra, y, cbcr, stream=None, wait=False):
         """bgra (F,H,W,4) -> y (F,H,Wp), cbcr (F,H/2,Cp)."""

@@ -175,8 +175,8 @@ def test_renderScaled_and_AAPLRenderer_policy(mrc):
     assert mrc.launchCount == n0 + 1
     assert np.array_equal(same.pixels, mid_want)
     big = mrc.makeBGRATexture(ow, oh)
-    assert ren.drawFrame(pb, None, big)                      # decode + rescale (AAPLRenderer.m:940-977), fused: one kernel
-    assert mrc.launchCount == n0 + 2
+    assert ren.drawFrame(pb, None, big)                      # two passes (AAPLRenderer.m:940-977)
+    assert mrc.launchCount == n0 + 3
     want = ORA.rescale_bgra(mid_want, ow, oh)
     assert np.array_equal(big.pixels, want)
     sc = r.MetalScaleRenderContext()

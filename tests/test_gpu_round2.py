@@ -409,12 +409,13 @@ def test_fused_decode_rescale_equals_decode_then_rescale(w, h, ow, oh, F, gamma)
     out = torch.zeros((F, oh, ow, 4), dtype=torch.uint8, device="cuda")
     C = ctx()
     n0 = C.launch_count
-    C.decode_rescale_nv12(gamma, ty, tc, scratch, out, wait=True)
+    if fused_fits_ := (F * h * w * 4 >= (int(64 * h / oh) + 12) * ((w * 4 + 255) // 256 * 256)):
+        C.decode_rescale_nv12_fused(gamma, ty, tc, scratch, out, wait=True)
+    else:
+        C.decode_rescale_nv12(gamma, ty, tc, scratch, out, wait=True)
     # one launch = the fused kernel.  (A scratch area smaller than one CTA slice - the 128x2 case: 3 KB - cannot host
     # it; the call then runs the two passes.)
-    slice_rows = int(64 * h / oh) + 8 + 2 + 2
-    fused_fits = F * h * w * 4 >= slice_rows * ((w * 4 + 255) // 256 * 256)
-    assert C.launch_count == n0 + (1 if fused_fits else 2), "expected the fused kernel (one launch)"
+    assert C.launch_count == n0 + (1 if fused_fits_ else 2), "expected the fused kernel (one launch)"
     got = out.cpu().numpy()
     for f in range(F):
         mid = ORA.decode_nv12(gamma, frames[f][0], frames[f][1])
@@ -422,9 +423,11 @@ def test_fused_decode_rescale_equals_decode_then_rescale(w, h, ow, oh, F, gamma)
         assert np.array_equal(got[f], want), f"frame {f}: {(got[f] != want).sum()} byte mismatches"
 
 
-def test_fused_falls_back_to_two_passes():
-    """alpha stream, ragged width, padded scratch rows or BT709_NO_FUSED: two kernels, same result"""
+def test_fused_entry_refuses_what_it_cannot_do_and_the_policy_entry_runs_two_passes():
+    """alpha stream / ragged width / padded scratch rows: the _fused entry returns BT709_E_UNSUPPORTED (-8), the policy
+    entry bt709_decode_rescale_nv12 runs the two kernels (also with a full-size scratch: faster on B200)"""
     from _gpu import ctx, dev
+    from metalbt709decoder_b200 import BT709Error
     C = ctx()
     w, h, ow, oh = 256, 64, 400, 100
     y, c = frame_random(w, h, seed=5)
@@ -439,11 +442,31 @@ def test_fused_falls_back_to_two_passes():
     assert np.array_equal(scratch[0].cpu().numpy(), mid)
     assert np.array_equal(out[0].cpu().numpy(), ORA.rescale_bgra(mid, ow, oh))
     padded = torch.zeros((1, h, w + 8, 4), dtype=torch.uint8, device="cuda")[:, :, :w]
+    with pytest.raises(BT709Error) as e:
+        C.decode_rescale_nv12_fused(3, ty, tc, padded, out)
+    assert e.value.status == -8
+    yr, cr = frame_random(130, 64, seed=7)
+    with pytest.raises(BT709Error) as e:
+        C.decode_rescale_nv12_fused(3, dev(yr)[None], dev(cr)[None], torch.zeros((1, 64, 130, 4), dtype=torch.uint8, device="cuda"), out)
+    assert e.value.status == -8
+    # full-size scratch: the policy entry decodes into it and rescales from it (two launches)
+    want = ORA.rescale_bgra(ORA.decode_nv12(3, y, c), ow, oh)
     n0 = C.launch_count
-    C.decode_rescale_nv12(3, ty, tc, padded, out, wait=True)
-    assert C.launch_count == n0 + 2
-    mid = ORA.decode_nv12(3, y, c)
-    assert np.array_equal(out[0].cpu().numpy(), ORA.rescale_bgra(mid, ow, oh))
+    C.decode_rescale_nv12(3, ty, tc, scratch, out, wait=True)
+    assert C.launch_count == n0 + 2 and np.array_equal(out[0].cpu().numpy(), want)
+    # two frames, scratch for one (frame stride 0): the fused entry works inside the first frame's area
+    F = 2
+    ty2, tc2 = ty.repeat(F, 1, 1), tc.repeat(F, 1, 1)
+    out2 = torch.zeros((F, oh, ow, 4), dtype=torch.uint8, device="cuda")
+    from metalbt709decoder_b200._lib import Plane
+    ps = Plane(scratch.data_ptr(), w * 4, 0)
+    py, pc, po = Plane(ty2.data_ptr(), w, w * h), Plane(tc2.data_ptr(), w, w * h // 2), Plane(out2.data_ptr(), ow * 4, ow * oh * 4)
+    n0 = C.launch_count
+    rc = C._L.bt709_decode_rescale_nv12_fused(C.handle, 3, ctypes.byref(py), ctypes.byref(pc), ctypes.byref(ps), ctypes.byref(po),
+                                              w, h, ow, oh, F, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream), 1)
+    assert rc == 0 and C.launch_count == n0 + 1
+    got = out2.cpu().numpy()
+    assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
 
 
 def test_fused_full_batch_checksum_against_two_passes():
@@ -463,6 +486,6 @@ def test_fused_full_batch_checksum_against_two_passes():
     got = torch.zeros_like(want)
     scratch = torch.empty((F, h, w, 4), dtype=torch.uint8, device="cuda")
     n0 = C.launch_count
-    C.decode_rescale_nv12(3, ty, tc, scratch, got, wait=True)
+    C.decode_rescale_nv12_fused(3, ty, tc, scratch, got, wait=True)
     assert C.launch_count == n0 + 1
     assert torch.equal(got, want)
