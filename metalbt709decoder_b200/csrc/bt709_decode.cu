@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
 //   * running 64-bit pointers (two adds per step each) instead of offset + wrap + LEA pairs.
 // COMPACT: no pad area in the stage (the 209 KB log-cell LUT of the Linear mode leaves room for 30 compact
 // ring slices); the idle lanes are then predicated off instead.
-template <int CL2, int RL2, bool ALPHA, int D, bool COMPACT>
+template <int CL2, int RL2, bool ALPHA, int D, bool COMPACT, bool EARLY>
 __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = CL2 > 0 ? 1 << CL2 : 1, R = 1 << RL2;
@@ -408,10 +408,20 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
 #pragma unroll
     for (int s = 0; s < D; s++) {
       if (kk + s >= nsteps) break;  // warp-uniform
-      asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
-      __syncwarp();  // the step's stage is complete for every lane, and every lane is done reading the previous one
-      if (kk + s + D - 1 < nsteps) issue((s + D - 1) % D);
-      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (EARLY) {
+        // the refill of the slot read one step ago is issued BEFORE waiting for this step's stage: two stages are in
+        // flight while the warp waits, one while it computes (measured: the access front of depth 3 with late issue
+        // spreads too far at full clock, 978 against 1017 Gpix/s in a 20-step burst)
+        if (kk + s + D - 1 < nsteps) issue((s + D - 1) % D);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 1) : "memory");
+        __syncwarp();
+      } else {
+        asm volatile("cp.async.wait_group %0;" ::"n"(D - 2) : "memory");
+        __syncwarp();  // the step's stage is complete for every lane, and every lane is done reading the previous one
+        if (kk + s + D - 1 < nsteps) issue((s + D - 1) % D);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
       const uint32_t st = st0 + s * kStage;
       TileLoad<ALPHA> t;
       t.y0 = lds_u32(st);
@@ -421,6 +431,7 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
         t.a0 = lds_u32(st + kAlphaOff);
         t.a1 = lds_u32(st + kAlphaOff + 128);
       }
+      if (EARLY) __syncwarp();  // every lane has its words before the next step refills this slot
       f32x2 cbn = mul2(add2(pku(magic_byte<0>(t.c), magic_byte<2>(t.c)), k.kC), k.inv255);
       f32x2 crn = mul2(add2(pku(magic_byte<1>(t.c), magic_byte<3>(t.c)), k.kC), k.inv255);
       f32x2 cb_g = mul2(cbn, k.g_cb), cb_b = mul2(cbn, k.b_cb);
@@ -774,21 +785,23 @@ static bool bulk_ok(const DecodeArgs &a, int *nstages, int *stage_bytes, int *nr
   return true;
 }
 
-#ifndef BT709_LIN_DEPTH
-#define BT709_LIN_DEPTH 3
-#endif
-constexpr int kLinDepth = BT709_LIN_DEPTH;  // stages of the per-warp cp.async ring of k_decode_lin
-
+// Ring of k_decode_lin: depth 2 with the refill issued BEFORE the wait ("2e": two stages in flight while the warp
+// waits, one while it computes) or depth 3 with the refill issued after it ("3l": two stages in flight throughout, one
+// __syncwarp less).  Measured on one box, 600 x 1080p, BT.709 curve, 20 / 100 / 1000 steps (Gpix/s):
+//   2e 1016 / 953 / 899     3l 994 / 973 / 918     round-1 ring kernel 1017 / 953 / 900
+// i.e. the deeper late-issue ring is 2 % slower in a burst at full clock (the access front spreads) and 2 % faster once
+// the power cap has pulled the clocks down.  The Linear mode and the alpha variant are faster with 3l either way
+// (Linear 1012 vs 966 in a burst).  BT709_RING=2e|3l overrides the choice.
 // k_decode_lin for a contiguous batch of full tiles (decoded as one tall image).  Returns -1 when it does not apply.
-template <int CL2, int RL2, bool ALPHA, bool COMPACT>
-static int launch_decode_lin(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
+template <int CL2, int RL2, bool ALPHA, bool COMPACT, int D, bool EARLY>
+static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
   DecodeArgs a = a0;
   a.h *= a.nframes;
   a.rows2 *= a.nframes;
   a.nframes = 1;
   const size_t lut_bytes = (((size_t) (CL2 > 0 ? (1 << CL2) + 1 : a.log_cells) * (1 << RL2) * 4) + 127) & ~(size_t) 127;
   if (lut_bytes >= kMaxDynSmem) return -1;
-  const size_t slice = (size_t) kLinDepth * (COMPACT ? (ALPHA ? 640 : 384) : (ALPHA ? 1024 : 512));
+  const size_t slice = (size_t) D * (COMPACT ? (ALPHA ? 640 : 384) : (ALPHA ? 1024 : 512));
   int wpc = (int) ((kMaxDynSmem - lut_bytes) / slice);
   if (wpc > 32) wpc = 32;
   if (wpc < 8) return -1;
@@ -801,8 +814,17 @@ static int launch_decode_lin(const DecodeArgs &a0, int sm_count, cudaStream_t s)
   a.lin_wpc = wpc;
   a.lin_warps = (int) (W / T * T);
   a.lin_drp = a.lin_warps / (int) T;
-  k_decode_lin<CL2, RL2, ALPHA, kLinDepth, COMPACT><<<(unsigned) grid, wpc * 32, lut_bytes + (size_t) wpc * slice, s>>>(a), note_launch();
+  k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY><<<(unsigned) grid, wpc * 32, lut_bytes + (size_t) wpc * slice, s>>>(a), note_launch();
   return (int) cudaGetLastError();
+}
+
+// ring choice: BT709_RING=2e|3l, else `late3_default` (see the table above)
+template <int CL2, int RL2, bool ALPHA, bool COMPACT>
+static int launch_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s, bool late3_default) {
+  static const char *env = getenv("BT709_RING");
+  const bool late3 = env ? (env[0] == '3') : late3_default;
+  if (late3) return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, 3, false>(a, sm_count, s);
+  return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, 2, true>(a, sm_count, s);
 }
 
 // Picks the k_decode_lin instantiation: per-lane replicated LUT for batches, a few replicas (a much shorter
@@ -832,19 +854,19 @@ static int try_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s) {
     b.log_cells = a.blog_cells;
     b.log_first = a.blog_first;
     b.log_bias = a.blog_bias;
-    if (small) return launch_decode_lin<-1, 2, ALPHA, false>(b, sm_count, s);
-    return launch_decode_lin<-1, 5, ALPHA, false>(b, sm_count, s);
+    if (small) return launch_decode_lin<-1, 2, ALPHA, false>(b, sm_count, s, true);
+    return launch_decode_lin<-1, 5, ALPHA, false>(b, sm_count, s, true);
   }
   if (a.log_lut && a.log_cells > 0) {
     DecodeArgs b = a;
     b.lut = a.log_lut;
     b.clamp_lo = a.log_clamp_lo;
-    if (small) return launch_decode_lin<0, 2, ALPHA, false>(b, sm_count, s);
-    return launch_decode_lin<0, 5, ALPHA, true>(b, sm_count, s);
+    if (small) return launch_decode_lin<0, 2, ALPHA, false>(b, sm_count, s, true);
+    return launch_decode_lin<0, 5, ALPHA, true>(b, sm_count, s, true);
   }
   if (a.cells_log2 == 10) {
-    if (small) return launch_decode_lin<10, 3, ALPHA, false>(a, sm_count, s);
-    return launch_decode_lin<10, 5, ALPHA, false>(a, sm_count, s);
+    if (small) return launch_decode_lin<10, 3, ALPHA, false>(a, sm_count, s, ALPHA);
+    return launch_decode_lin<10, 5, ALPHA, false>(a, sm_count, s, ALPHA);
   }
   return -1;
 }
@@ -970,22 +992,40 @@ static int optin_decode_smem_log() {
   e = (int) cudaFuncSetAttribute(k_decode_ring<0, 5, ALPHA, true, kRingDepth, kDecodeThreads>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
   if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_decode_lin<0, 5, ALPHA, kLinDepth, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = (int) cudaFuncSetAttribute(k_decode_lin<0, 5, ALPHA, 2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int) kMaxDynSmem);
   if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_decode_lin<0, 2, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = (int) cudaFuncSetAttribute(k_decode_lin<0, 5, ALPHA, 3, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int) kMaxDynSmem);
   if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_decode_lin<-1, 5, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = (int) cudaFuncSetAttribute(k_decode_lin<0, 2, ALPHA, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int) kMaxDynSmem);
   if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_decode_lin<-1, 2, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = (int) cudaFuncSetAttribute(k_decode_lin<0, 2, ALPHA, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int) kMaxDynSmem);
   if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_decode_lin<10, 5, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = (int) cudaFuncSetAttribute(k_decode_lin<-1, 5, ALPHA, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int) kMaxDynSmem);
   if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_decode_lin<10, 3, ALPHA, kLinDepth, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  e = (int) cudaFuncSetAttribute(k_decode_lin<-1, 5, ALPHA, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<-1, 2, ALPHA, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<-1, 2, ALPHA, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<10, 5, ALPHA, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<10, 5, ALPHA, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<10, 3, ALPHA, 2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_lin<10, 3, ALPHA, 3, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int) kMaxDynSmem);
   if (e) return e;
   return (int) cudaFuncSetAttribute(k_decode_ring<0, 5, ALPHA, false, kRingDepth, kDecodeThreads>,

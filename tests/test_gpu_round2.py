@@ -239,10 +239,12 @@ def test_linear_tile_stream_kernel(w, h, F, gamma, alpha):
         assert np.array_equal(got[f], want), f"{w}x{h} frame {f}: {(got[f] != want).sum()} byte mismatches"
 
 
-@pytest.mark.parametrize("env", [{"BT709_SMALL_STEPS": "0"}, {"BT709_SMALL_STEPS": "1000000"}, {"BT709_NO_LIN2": "1"}])
+@pytest.mark.parametrize("env", [{"BT709_SMALL_STEPS": "0"}, {"BT709_SMALL_STEPS": "1000000"}, {"BT709_NO_LIN2": "1"},
+                                 {"BT709_RING": "3l"}, {"BT709_RING": "2e"}, {"BT709_FUSED": "1"}])
 def test_decode_lut_replication_variants_in_a_subprocess(env):
     """BT709_SMALL_STEPS=0: the per-lane replicated LUT even for tiny calls; =1000000: the few-replica LUT even for
-    batches; BT709_NO_LIN2: the round-1 kernels.  Each must stay exact (env is read once per process)."""
+    batches; BT709_NO_LIN2: the round-1 kernels; BT709_RING: both ring variants of k_decode_lin for every mode;
+    BT709_FUSED: the policy entry takes the fused kernel.  Each must stay exact (env is read once per process)."""
     code = r'''
 import sys, numpy as np, torch
 sys.path.insert(0, "tests")
@@ -259,6 +261,12 @@ for (w, h, F, g, al) in [(1920, 64, 2, 3, False), (3840, 8, 3, 2, False), (2048,
     got = out.cpu().numpy()
     for f in range(F):
         assert np.array_equal(got[f], ora.decode_nv12(g, fr[f][0], fr[f][1], alpha_y=al_np[f] if al else None)), (w, h, g, f)
+from _oracle import bgra_random
+w, h, ow, oh = 256, 64, 400, 100
+y, c = frame_random(w, h, seed=91)
+out = torch.zeros((1, oh, ow, 4), dtype=torch.uint8, device="cuda")
+ctx().decode_rescale_nv12(3, dev(y)[None], dev(c)[None], torch.zeros((1, h, w, 4), dtype=torch.uint8, device="cuda"), out, wait=True)
+assert np.array_equal(out[0].cpu().numpy(), ora.rescale_bgra(ora.decode_nv12(3, y, c), ow, oh))
 print("variant ok")
 '''
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, **env), capture_output=True, text=True,
