@@ -785,6 +785,77 @@ static bool bulk_ok(const DecodeArgs &a, int *nstages, int *stage_bytes, int *nr
   return true;
 }
 
+// ================================================================= decode, linear tile stream, register loads
+// Same tile order and constant strides as k_decode_lin, but the three words of a tile come straight into registers
+// (LDG.32 x 3) with the loads of the next PD tiles in flight, instead of through the cp.async ring.  The r2 probe
+// tools/probes/row_bw.cu measured this pattern (no arithmetic) at 1050 Gpix/s with two units in flight against 1009
+// for the ring.  No shared memory beyond the LUT, no __syncwarp.  Opaque only (the alpha variant keeps the ring).
+template <int CL2, int RL2, int PD>
+__global__ void __launch_bounds__(1024, 1) k_decode_reg(const DecodeArgs p) {
+  extern __shared__ __align__(128) uint32_t s_lut[];
+  constexpr int N = CL2 > 0 ? 1 << CL2 : 1, R = 1 << RL2;
+  const int entries = CL2 > 0 ? N + 1 : p.log_cells;
+  for (int i = threadIdx.x; i < entries * R; i += blockDim.x) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const unsigned warp = threadIdx.x >> 5;
+  const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_lut);
+  const uint32_t sbase = smem0 + ((lane & (R - 1)) << 2) - ((CL2 > 0 ? 0x4B000000u : p.log_first) << (2 + RL2));
+  const float clamp_lo = p.clamp_lo;
+  DecodeK2 k;
+  k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
+  k.kC = pk(-(8388608.0f + 128.0f), -(8388608.0f + 128.0f));
+  k.inv255 = pk(p.m.inv255, p.m.inv255);
+  k.ys = pk(p.m.ys, p.m.ys);
+  k.g_cb = pk(p.m.g_cb, p.m.g_cb);
+  k.b_cb = pk(p.m.b_cb, p.m.b_cb);
+  k.r_cr = pk(p.m.r_cr, p.m.r_cr);
+  k.g_cr = pk(p.m.g_cr, p.m.g_cr);
+  k.fN = pk((float) N, (float) N);
+  k.magic = pk(8388608.0f, 8388608.0f);
+  k.one = pk(p.one, p.one);
+  k.bias = pk(p.log_bias, p.log_bias);
+
+  const unsigned g = blockIdx.x * (unsigned) p.lin_wpc + warp;
+  if (g >= (unsigned) p.lin_warps) return;
+  const unsigned T = (unsigned) p.tiles_per_row, rows2 = (unsigned) p.rows2, drp = (unsigned) p.lin_drp;
+  const unsigned rp0 = g / T, tile = g - rp0 * T;
+  if (rp0 >= rows2) return;
+  const unsigned nsteps = (rows2 - rp0 + drp - 1) / drp;
+  const uint8_t *yp = p.y + (long long) rp0 * 2 * p.py + (size_t) (tile * 32 + lane) * 4;
+  const uint8_t *cp = p.c + (long long) rp0 * p.pc + (size_t) (tile * 32 + lane) * 4;
+  const long long py = p.py, yinc = (long long) drp * 2 * p.py, cinc = (long long) drp * p.pc;
+  uint8_t *out0 = p.out + (long long) rp0 * 2 * p.po + (size_t) (tile * 32 + lane) * 16;
+  const long long po = p.po, oinc = (long long) drp * 2 * p.po;
+  constexpr int NB = PD + 1;
+  TileLoad<false> buf[NB];
+  auto load = [&](TileLoad<false> &t) {
+    t.y0 = ld_stream_u32(yp);
+    t.y1 = ld_stream_u32(yp + py);
+    t.c = ld_stream_u32(cp);
+    yp += yinc;
+    cp += cinc;
+  };
+#pragma unroll
+  for (int j = 0; j < PD; j++)
+    if ((unsigned) j < nsteps) load(buf[j]);
+  for (unsigned kk = 0; kk < nsteps; kk += NB) {
+#pragma unroll
+    for (int s = 0; s < NB; s++) {
+      if (kk + s >= nsteps) break;  // warp-uniform
+      if (kk + s + PD < nsteps) load(buf[(s + PD) % NB]);
+      const TileLoad<false> &t = buf[s];
+      f32x2 cbn = mul2(add2(pku(magic_byte<0>(t.c), magic_byte<2>(t.c)), k.kC), k.inv255);
+      f32x2 crn = mul2(add2(pku(magic_byte<1>(t.c), magic_byte<3>(t.c)), k.kC), k.inv255);
+      f32x2 cb_g = mul2(cbn, k.g_cb), cb_b = mul2(cbn, k.b_cb);
+      f32x2 cr_r = mul2(crn, k.r_cr), cr_g = mul2(crn, k.g_cr);
+      st_stream_u128(out0, decode_row<CL2, RL2, false>(t.y0, 0u, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+      st_stream_u128(out0 + po, decode_row<CL2, RL2, false>(t.y1, 0u, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+      out0 += oinc;
+    }
+  }
+}
+
 // Ring of k_decode_lin: depth 2 with the refill issued BEFORE the wait ("2e": two stages in flight while the warp
 // waits, one while it computes) or depth 3 with the refill issued after it ("3l": two stages in flight throughout, one
 // __syncwarp less).  Measured on one box, 600 x 1080p, BT.709 curve, 20 / 100 / 1000 steps (Gpix/s):
@@ -822,6 +893,26 @@ static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s
 template <int CL2, int RL2, bool ALPHA, bool COMPACT>
 static int launch_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s, bool late3_default) {
   static const char *env = getenv("BT709_RING");
+  static const char *reg_env = getenv("BT709_REG");  // experiment: register loads, 1-3 tiles ahead (opaque, replicated LUT)
+  if constexpr (!ALPHA && !COMPACT && RL2 == 5) {
+    if (reg_env) {
+      DecodeArgs b = a;
+      b.h *= b.nframes; b.rows2 *= b.nframes; b.nframes = 1;
+      const size_t lut_bytes = (((size_t) (CL2 > 0 ? (1 << (CL2 > 0 ? CL2 : 0)) + 1 : b.log_cells) * 32 * 4) + 127) & ~(size_t) 127;
+      const unsigned T = (unsigned) b.tiles_per_row;
+      unsigned long long grid = ((unsigned long long) b.rows2 * T + 31) / 32;
+      if (grid > (unsigned long long) sm_count) grid = sm_count;
+      const unsigned W = (unsigned) grid * 32;
+      if (W >= T) {
+        b.lin_wpc = 32; b.lin_warps = (int) (W / T * T); b.lin_drp = b.lin_warps / (int) T;
+        const int pd = atoi(reg_env);
+        if (pd == 1) k_decode_reg<CL2, RL2, 1><<<(unsigned) grid, 1024, lut_bytes, s>>>(b), note_launch();
+        else if (pd == 3) k_decode_reg<CL2, RL2, 3><<<(unsigned) grid, 1024, lut_bytes, s>>>(b), note_launch();
+        else k_decode_reg<CL2, RL2, 2><<<(unsigned) grid, 1024, lut_bytes, s>>>(b), note_launch();
+        return (int) cudaGetLastError();
+      }
+    }
+  }
   const bool late3 = env ? (env[0] == '3') : late3_default;
   if (late3) return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, 3, false>(a, sm_count, s);
   return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, 2, true>(a, sm_count, s);
@@ -1054,10 +1145,21 @@ static int optin_decode_smem() {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
 }
 
+template <int CL2, int RL2>
+static int optin_decode_reg() {
+  int e = (int) cudaFuncSetAttribute(k_decode_reg<CL2, RL2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  e = (int) cudaFuncSetAttribute(k_decode_reg<CL2, RL2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+  if (e) return e;
+  return (int) cudaFuncSetAttribute(k_decode_reg<CL2, RL2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+}
+
 // per device (called from bt709_ctx_create with the device current): opt in to > 48 KB of dynamic
 // shared memory for the replicated-LUT decode kernels
 int decode_kernels_init() {
   int e;
+  if ((e = optin_decode_reg<10, 5>())) return e;
+  if ((e = optin_decode_reg<-1, 5>())) return e;
   if ((e = optin_decode_smem<10, 5, false>())) return e;
   if ((e = optin_decode_smem<10, 5, true>())) return e;
   if ((e = optin_decode_smem<12, 3, false>())) return e;
