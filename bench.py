@@ -523,8 +523,17 @@ def run_e2e(args, ctx, device, w, h, frames, gamma):
             assert ok
         assert mrc.waitUntilCompleted()
 
+    import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized()
+
+    def rank_barrier():
+        # all ranks start a timed leg together: they share one host and its PCIe root, which is what limits this leg
+        torch.cuda.synchronize()
+        if multi:
+            dist.barrier()
+
     one_pass()
-    torch.cuda.synchronize()
+    rank_barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
         one_pass()
@@ -532,7 +541,7 @@ def run_e2e(args, ctx, device, w, h, frames, gamma):
     secs = time.perf_counter() - t0
     # ---- the ceiling of this call pattern: the same bytes over PCIe with no kernel in between (pinned host buffers,
     # one H2D of a frame's NV12 planes and one D2H of its BGRA image per frame, same 4 streams)
-    copy_secs = None
+    copy_secs, copy_pass = None, None
     try:
         hin = [torch.empty(w * h * 3 // 2, dtype=torch.uint8).pin_memory() for _ in range(4)]
         hout = [torch.empty(w * h * 4, dtype=torch.uint8).pin_memory() for _ in range(4)]
@@ -550,12 +559,14 @@ def run_e2e(args, ctx, device, w, h, frames, gamma):
                 s_.synchronize()
 
         copy_pass()
+    except Exception:
+        copy_pass = None
+    rank_barrier()  # every rank reaches this, whether or not its buffers could be allocated
+    if copy_pass is not None:
         t1 = time.perf_counter()
         for _ in range(steps):
             copy_pass()
         copy_secs = time.perf_counter() - t1
-    except Exception:
-        copy_secs = None
     # the host path must have produced what the (parity-tested) device-resident kernel produces for the same frames
     verified = True
     for i in (0, ring - 1):

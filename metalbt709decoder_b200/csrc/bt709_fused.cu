@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(const FusedArgs a
   } else {
     sbase = c.enc_base;  // cvta(encode LUT) - (first << 7) + (lane << 2): exactly the <-1, 5> lookup base
   }
+  asm volatile("" : "+r"(sbase));  // one register, not a base + constant that ptxas re-adds at every lookup
   const float clamp_lo = d.clamp_lo;
   DecodeK2 k;
   k.kY = pk(-(8388608.0f + 16.0f), -(8388608.0f + 16.0f));
