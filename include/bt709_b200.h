@@ -145,7 +145,7 @@ BT709_API int bt709_decode_rescale_nv12(const bt709_ctx *ctx, bt709_gamma gamma,
  * ((64 h / out_h + 12) rows; frames back to back: the whole batch-sized area is used, one slice per SM; any other
  * frame stride: only the first frame's area); returns BT709_E_UNSUPPORTED otherwise.  bt709_decode_rescale_nv12 itself
  * takes this path when the environment variable BT709_FUSED is set.
- * Measured on B200 (1080p -> 1440p): 39 % less DRAM traffic, 13 % lower frame rate than the two kernels (both
+ * Measured on B200 (1080p -> 1440p): 39 % less DRAM traffic, 12 % lower frame rate than the two kernels (both
  * halves are instruction-bound), see DESIGN.md section 4.4. */
 BT709_API int bt709_decode_rescale_nv12_fused(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane *y,
                                               const bt709_plane *cbcr, const bt709_plane *scratch,

@@ -379,7 +379,7 @@ int bt709_decode_rescale_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt7
   if (!ctx) return BT709_E_NULL;
   if (!scratch || !scratch->ptr) return BT709_E_SCRATCH;
   // The fused kernel (one launch, the intermediate stays in L2: 39 % less HBM traffic) is bit-identical but measured
-  // 13 % slower than the two launches on 1080p -> 1440p, because both halves are instruction-bound, not HBM-bound
+  // 12 % slower than the two launches on 1080p -> 1440p, because both halves are instruction-bound, not HBM-bound
   // (DESIGN.md section 4.4): it runs when asked for (the _fused entry, or BT709_FUSED=1 in the environment).
   static const bool prefer_fused = getenv("BT709_FUSED") != nullptr;
   if (prefer_fused) {
