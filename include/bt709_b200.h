@@ -99,6 +99,8 @@ BT709_API unsigned long long bt709_launch_count(const bt709_ctx *ctx);
 /* Host-only self-check of the constant tables (needs no GPU; used by tests/test_tables_cpu.py):
  *   1. for every gamma mode and every one of the 2^24 (Y,Cb,Cr) inputs, the cell-LUT lookup of the
  *      G-channel matrix output equals the direct double-precision evaluation of the curve;
+ *   1b. the biased log-cell LUT of the sRGB encode equals the step function around every threshold and cell
+ *      boundary and on 4 M floats spread over [0, 1];
  *   2. the three-instruction constant division of the encode path equals IEEE division for every
  *      8-bit RGB triple.
  * Returns 0 on success, else the 1-based index of the first failing check. */

@@ -324,6 +324,35 @@ int selftest_host() {
     for (auto &x : th) x.join();
     if (bad.load()) return 3;
   }
+  // 1b. biased log-cell LUT of the sRGB encode (pass 2, fused kernel, Linear-mode decode) == the step function:
+  //     every float within 64 ulp of a threshold or of a cell boundary, and 4 M floats spread over [0, 1]
+  //     (the exhaustive sweep over all 1.07e9 floats of [0, 1] was run once at development time: 0 mismatches)
+  {
+    StepFn fn;
+    BiasedLogLut bl;
+    if (!build_step_fn(decode_code, kLinear, &fn)) return 1;
+    if (!build_biased_log_lut(fn, 1.0f / 32.0f, &bl)) return 10;
+    long bad = 0;
+    auto check = [&](uint32_t bits) {
+      if (bits > 0x3F800000u) return;
+      const float x = u2f(bits);
+      if (biased_log_lut_eval(bl, x) != fn.eval(x)) bad++;
+    };
+    for (int k = 1; k <= 255; k++)
+      if (fn.thr[k] <= 1.0f)
+        for (int d = -64; d <= 64; d++) check(f2u(fn.thr[k]) + d);
+    // cell boundaries: the first x whose biased value lands in each cell
+    for (uint32_t c = bl.first; c < bl.first + (uint32_t) bl.entries.size(); c++) {
+      uint32_t lo = 0, hi = 0x3F800000u;
+      while (hi - lo > 1) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if ((f2u(u2f(mid) + bl.bias) >> 16) >= c) hi = mid; else lo = mid;
+      }
+      for (int d = -64; d <= 64; d++) check(hi + d);
+    }
+    for (uint32_t b = 0; b <= 0x3F800000u; b += 263) check(b);
+    if (bad) return 11;
+  }
   // 2. x / c == fma(fma(-q0, c, x), rc, q0), q0 = x * rc, for every value the 4:2:0 encode divides
   {
     const float Kr = 0.2126f, Kg = 0.7152f, Kb = 0.0722f, cb = 1.8556f, cr = 1.5748f;
