@@ -30,8 +30,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_status_strings():
     L = _lib.lib()
-    for s in range(0, -8, -1):
-        assert L.bt709_status_string(s)
+    for s in range(0, -9, -1):
+        assert L.bt709_status_string(s) and b"unknown" not in L.bt709_status_string(s)
     assert b"unknown" in L.bt709_status_string(-99)
 
 
@@ -51,6 +51,9 @@ def test_null_arguments_are_rejected_not_crashed():
     assert L.bt709_rescale_bgra(None, None, 2, 2, None, 2, 2, 1, None, 0) == -1
     assert L.bt709_encode_bgra_to_nv12(None, 1, 0, None, None, None, 2, 2, 1, None, 0) == -1
     assert L.bt709_convert_packed444(None, None, None, 2, 2, None, 0) == -1
+    assert L.bt709_convert_packed444_gamma(None, 3, None, None, 2, 2, None, 0) == -1
+    assert L.bt709_unconvert_packed444_gamma(None, 3, None, None, 2, 2, None, 0) == -1
+    assert L.bt709_decode_rescale_nv12_fused(None, 0, None, None, None, None, 2, 2, 4, 4, 1, None, 0) == -1
     assert L.bt709_launch_count(None) == 0
 
 
