@@ -298,10 +298,8 @@ def make_step(ctx, d, kind, gamma, stream):
     if kind == "rescale":
         return lambda: ctx.rescale_bgra(d["src"], d["big"], stream=stream)
     if kind == "twopass":
-        def two():
-            ctx.decode_nv12(gamma, d["y"], d["c"], d["out"], stream=stream)
-            ctx.rescale_bgra(d["out"], d["big"], stream=stream)
-        return two
+        # the policy entry (AAPLRenderer.m:940-977): pass 1 into the same-size intermediate, pass 2 out of it
+        return lambda: ctx.decode_rescale_nv12(gamma, d["y"], d["c"], d["out"], d["big"], stream=stream)
     if kind == "fused":
         return lambda: ctx.decode_rescale_nv12_fused(gamma, d["y"], d["c"], d["scratch"], d["big"], stream=stream)
     if kind == "encode":

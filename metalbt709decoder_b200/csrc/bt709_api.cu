@@ -274,8 +274,16 @@ int bt709_decode_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt709_plane
   return finish(ctx, l0, launch_decode(a, ctx->sm_count, stream), stream, wait);
 }
 
+static int rescale_impl(const bt709_ctx *ctx, const bt709_plane *in, int in_w, int in_h, const bt709_plane *out,
+                        int out_w, int out_h, int nframes, void *stream, int wait, int known_opaque);
+
 int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, int in_h, const bt709_plane *out,
                        int out_w, int out_h, int nframes, void *stream, int wait) {
+  return rescale_impl(ctx, in, in_w, in_h, out, out_w, out_h, nframes, stream, wait, 0);
+}
+
+static int rescale_impl(const bt709_ctx *ctx, const bt709_plane *in, int in_w, int in_h, const bt709_plane *out,
+                        int out_w, int out_h, int nframes, void *stream, int wait, int known_opaque) {
   if (!ctx || !plane_ok(in) || !plane_ok(out)) return BT709_E_NULL;
   if (in_w <= 0 || in_h <= 0 || out_w <= 0 || out_h <= 0 || nframes <= 0) return BT709_E_DIMS;
   int rc;
@@ -288,6 +296,7 @@ int bt709_rescale_bgra(const bt709_ctx *ctx, const bt709_plane *in, int in_w, in
   if (!guard.ok) return cuda_fail(ctx, cudaErrorInvalidDevice);
   RescaleArgs a{};
   fill_rescale_args(ctx, in, in_w, in_h, out, out_w, out_h, nframes, &a);
+  a.known_opaque = known_opaque;
   const unsigned long long l0 = launches_begin();
   return finish(ctx, l0, launch_rescale(a, ctx->sm_count, stream), stream, wait);
 }
@@ -389,7 +398,8 @@ int bt709_decode_rescale_nv12(const bt709_ctx *ctx, bt709_gamma gamma, const bt7
   // AAPLRenderer.m:940-977: decode into the same-size sRGB intermediate, then rescale
   int rc = bt709_decode_nv12(ctx, gamma, y, cbcr, alpha_y, scratch, w, h, nframes, stream, 0);
   if (rc) return rc;
-  return bt709_rescale_bgra(ctx, scratch, w, h, bgra_out, out_w, out_h, nframes, stream, wait);
+  // without an alpha stream pass 1 has just written A = 255 everywhere (AAPLShaders.metal:243): pass 2 need not watch for alpha
+  return rescale_impl(ctx, scratch, w, h, bgra_out, out_w, out_h, nframes, stream, wait, alpha_y == nullptr);
 }
 
 int bt709_encode_bgra_to_nv12(const bt709_ctx *ctx, bt709_gamma gin, bt709_gamma gout, const bt709_plane *in,

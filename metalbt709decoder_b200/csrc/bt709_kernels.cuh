@@ -74,6 +74,7 @@ struct RescaleArgs {
   int enc_blog_cells;
   unsigned enc_blog_first;
   float one;  // 1.0f, deliberately a runtime value (blocks FFMA2 contraction, see k_rescale_cols)
+  int known_opaque;  // the caller guarantees A = 255 everywhere (pass 1 without an alpha stream wrote the source)
 };
 
 struct EncodeArgs {

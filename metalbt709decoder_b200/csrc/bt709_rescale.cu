@@ -478,7 +478,9 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) k_rescale_pair(const Resca
         if (ox0 + q * 64 < p.ow) opaque = pair_tile<true, true, 1, true, kPairPD>(p, c, src, pi, dst, ox0 + q * 64, oy0, lane) && opaque;
       return opaque;
     };
-    if (!with_alpha) {
+    if (p.known_opaque) {  // the source was written by pass 1 without an alpha stream: nothing to watch for
+      pair_tile<false, true, kPairNP, false, kPairPD>(p, c, src, pi, dst, ox0, oy0, lane);
+    } else if (!with_alpha) {
       if (!pair_tile<false, true, kPairNP, true, kPairPD>(p, c, src, pi, dst, ox0, oy0, lane)) {  // a tap with A != 255: redo with alpha
         alpha_tile();
         with_alpha = true;
