@@ -142,10 +142,7 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   const int nl = (1 << p.out_cells_log2) + 1;
   for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
     const int b = i >> 5;
-    if (ONEVAL)  // same 256-byte entry stride, replicas 4 bytes apart in its first half: consecutive lanes, consecutive banks
-      reinterpret_cast<float *>(s_tab)[b * 64 + (i & 31)] = __ldg(&p.lin256[b]);
-    else
-      s_tab[i] = make_float2(__ldg(&p.lin256[b]), __ldg(&p.compn256[b]));
+    s_tab[i] = make_float2(__ldg(&p.lin256[b]), __ldg(&p.compn256[b]));
   }
   // chroma cell LUT replicated 8x (entry i replica r at word i*8 + r): random means otherwise
   // cost ~3 wavefronts per lookup and the kernel is bound by shared-memory bandwidth
@@ -155,7 +152,7 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   const int lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
   const uint32_t tab = (uint32_t) __cvta_generic_to_shared(s_tab);  // warp-uniform
-  const uint32_t lane8 = ONEVAL ? lane << 2 : lane << 3;  // byte offset of this lane's replica inside a table entry
+  const uint32_t lane8 = lane << 3;
   const uint32_t olut = (uint32_t) __cvta_generic_to_shared(s_olut) + ((lane & 7) << 2) - (0x4B000000u << 5);
   const float clamp_lo = p.out_clamp_lo;
   const float fN = (float) (1 << p.out_cells_log2);
