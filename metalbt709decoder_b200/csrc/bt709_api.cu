@@ -47,7 +47,6 @@ struct bt709_ctx {
   int fl_cells[3] = {};
   const float *lin256[3] = {};       // BT709_tolinearNorm per input gamma
   const float *compn256[3][3] = {};  // [gin][gout] unorm8(from_linear(to_linear(b)))
-  bool compn_is_lin[3][3] = {};       // the two tables are bit-identical (Linear -> Linear): one lookup serves both
   // per-pixel 4:4:4 encoders: sRGB byte -> non-linear value fed to the matrix, per bt709_gamma
   // (BT709.h:610-664 BT.709 curve, :743-817 Apple curve, :914-944 sRGB = byteNorm; Linear has no such encoder)
   const float *enc444[5] = {};
@@ -178,13 +177,7 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
   for (int gi = 0; gi < 3; gi++)
     for (int go = 0; go < 3; go++) {
       float t[256];
-      bool same = true;
-      for (int b = 0; b < 256; b++) {
-        t[b] = from_linear_code(go, to_linear(gi, b)) * (1.0f / 255.0f);
-        const float l = to_linear(gi, b);
-        same = same && std::memcmp(&t[b], &l, 4) == 0;
-      }
-      ctx->compn_is_lin[gi][go] = same;
+      for (int b = 0; b < 256; b++) t[b] = from_linear_code(go, to_linear(gi, b)) * (1.0f / 255.0f);
       off_comp[gi][go] = blob.add(t, 256);
     }
   for (int g = 0; g < 5; g++) {
@@ -430,7 +423,6 @@ int bt709_encode_bgra_to_nv12(const bt709_ctx *ctx, bt709_gamma gin, bt709_gamma
   a.lin256 = ctx->lin256[gin];
   a.compn256 = ctx->compn256[gin][gout];
   a.out_lut = ctx->fl_lut[gout]; a.out_clamp_lo = ctx->fl_clamp[gout]; a.out_cells_log2 = ctx->fl_cells[gout];
-  a.oneval = ctx->compn_is_lin[gin][gout] ? 1 : 0;  // verified bit-identical at context creation (Linear -> Linear)
   const unsigned long long l0 = launches_begin();
   return finish(ctx, l0, launch_encode(a, ctx->sm_count, stream), stream, wait);
 }

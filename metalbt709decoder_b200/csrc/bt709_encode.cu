@@ -130,10 +130,7 @@ __device__ __forceinline__ f32x2 add2_nc(f32x2 a, f32x2 b, const EncK &k) { retu
 
 // FULL = (w % 128 == 0): no per-lane predicates; otherwise the lanes past the row end load nothing and store nothing
 // WIDE: rows of more than 32 tiles (4096 pixels): the warps loop over the tile columns, 32 apart
-// ONEVAL: the two table values are the same number (Linear -> Linear: to_linear(b) = b/255 = the requantised value / 255,
-// the gamma pair of the alpha stream, srgb_to_bt709.m:842-954): a 4-byte table and one LDS.32 per channel byte, which
-// halves the shared-memory traffic that binds this kernel
-template <bool WRAP, bool FULL, bool WIDE, bool ONEVAL>
+template <bool WRAP, bool FULL, bool WIDE>
 __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
   // [0, 64 KB): float2 table, entry b replica r at byte b*256 + r*8;  then the chroma cell LUT
@@ -177,12 +174,7 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
     // table offset (byte << 8) | (lane << 3): byte 1 = the pixel's channel byte, byte 0 = lane * 8
     const uint32_t off = __byte_perm(px, lane8, shift == 16 ? 0x7724 : shift == 8 ? 0x7714 : 0x7704);  // bytes 2,3 = 0 (upper bytes of lane8)
     float2 v;
-    if (ONEVAL) {
-      asm("ld.shared.f32 %0, [%1];" : "=f"(v.x) : "r"(tab + off));
-      v.y = v.x;
-    } else {
-      asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(tab + off));
-    }
+    asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(tab + off));
     lin = v.x;
     cn = v.y;
   };
@@ -348,15 +340,10 @@ static int launch_encode_fast1(const EncodeArgs &a0, int sm_count, cudaStream_t 
   // The looping instantiation is also valid for narrower rows (its loop runs once) and its code schedule measured
   // faster when all 32 warps have a tile (2048 wide: 905 vs 883 Gpix/s), slower with 30 (1920 wide: 881 vs 916).
   const bool wide = a.tiles_per_row > wpc || wpc % a.tiles_per_row == 0;
-#define BT709_ENC_LAUNCH(W, F)                                                                       \
-  do {                                                                                               \
-    if (a.oneval) {                                                                                  \
-      if (wide) k_encode_fast<W, F, true, true><<<grid, 1024, smem, s>>>(a), note_launch();          \
-      else k_encode_fast<W, F, false, true><<<grid, 1024, smem, s>>>(a), note_launch();              \
-    } else {                                                                                         \
-      if (wide) k_encode_fast<W, F, true, false><<<grid, 1024, smem, s>>>(a), note_launch();         \
-      else k_encode_fast<W, F, false, false><<<grid, 1024, smem, s>>>(a), note_launch();             \
-    }                                                                                                \
+#define BT709_ENC_LAUNCH(W, F)                                                      \
+  do {                                                                              \
+    if (wide) k_encode_fast<W, F, true><<<grid, 1024, smem, s>>>(a), note_launch();                \
+    else k_encode_fast<W, F, false><<<grid, 1024, smem, s>>>(a), note_launch();                    \
   } while (0)
   if (wrap) {
     if (full) BT709_ENC_LAUNCH(true, true); else BT709_ENC_LAUNCH(true, false);
@@ -394,13 +381,9 @@ int launch_encode(const EncodeArgs &a, int sm_count, void *stream) {
 template <bool W, bool F>
 static int optin_encode_smem() {
   const int smem = 65536 + 4097 * 32;
-  int e = (int) cudaFuncSetAttribute(k_encode_fast<W, F, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int e = (int) cudaFuncSetAttribute(k_encode_fast<W, F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_encode_fast<W, F, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e) return e;
-  e = (int) cudaFuncSetAttribute(k_encode_fast<W, F, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e) return e;
-  return (int) cudaFuncSetAttribute(k_encode_fast<W, F, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  return (int) cudaFuncSetAttribute(k_encode_fast<W, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
 }
 
 int encode_kernels_init() {

@@ -92,7 +92,6 @@ struct EncodeArgs {
   unsigned step_rp, d_rp, pi16, py4, pc4, si16, sy4, sc4, di, dy, dc, wi, wy, wc;
   float one;  // 1.0f, deliberately a runtime value
   unsigned zero;  // 0, deliberately a runtime value (scheduling fence by data dependence, see k_encode_fast)
-  int oneval;     // lin256 and compn256 hold the same values (Linear -> Linear): one table word per channel byte
 };
 
 struct Packed444Args {
