@@ -65,7 +65,7 @@ class ClockSampler:
     """nvidia-smi sampler running during the timed region (B200_PROFILING.md clocks line)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,clocks.mem")
 
     def __init__(self, index, lms=100):
         self.index = index
@@ -96,7 +96,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, mem, pw = [], [], set(), [], []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
@@ -110,10 +110,21 @@ class ClockSampler:
             for n, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
+            try:
+                pw.append(float(f[3]))
+                if len(f) > 9:
+                    mem.append(float(f[9]))
+            except ValueError:
+                pass
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        if mem:
+            out["mem_mhz"] = sorted(mem)[len(mem) // 2]
+        if pw:
+            out["power_w_max"] = max(pw)
+        return out
 
 
 def measured_peak_gbs():
