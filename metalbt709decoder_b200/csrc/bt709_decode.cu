@@ -330,8 +330,11 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   const uint32_t kLutBytes = ((uint32_t) entries * R * 4 + 127u) & ~127u;
   // Y0 | Y1 | CbCr | pad (| A0 | A1 | pad | pad), 128 B each; COMPACT: without the pads
   constexpr uint32_t kStage = COMPACT ? (ALPHA ? 640 : 384) : (ALPHA ? 1024 : 512), kAlphaOff = COMPACT ? 384 : 512;
-  for (int i = threadIdx.x; i < entries * R; i += blockDim.x) s_lut[i] = __ldg(&p.lut[i >> RL2]);
-  __syncthreads();
+  // Programmatic dependent launch (small calls, launch_decode_lin1): let the next launch of the stream be scheduled
+  // now, and wait here until the previous kernel of the stream has completed and its writes are visible.  Both are
+  // no-ops for a launch without the attribute.  Nothing above this line touches global memory.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
@@ -354,11 +357,10 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   k.bias = pk(p.log_bias, p.log_bias);
 
   const unsigned g = blockIdx.x * (unsigned) p.lin_wpc + warp;
-  if (g >= (unsigned) p.lin_warps) return;
   const unsigned T = (unsigned) p.tiles_per_row, rows2 = (unsigned) p.rows2, drp = (unsigned) p.lin_drp;
   const unsigned rp0 = g / T, tile = g - rp0 * T;
-  if (rp0 >= rows2) return;
-  const unsigned nsteps = (rows2 - rp0 + drp - 1) / drp;
+  // (a warp without work still fills its share of the LUT and meets the CTA barrier below)
+  const unsigned nsteps = g < (unsigned) p.lin_warps && rp0 < rows2 ? (rows2 - rp0 + drp - 1) / drp : 0u;
 
   // ---- copy role of this lane: lanes 0-7 Y row 0, 8-15 Y row 1, 16-23 the CbCr row, 24-31 zero fill
   const int role = lane >> 3, sub = lane & 7;
@@ -403,6 +405,10 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
     if ((unsigned) j < nsteps) issue(j);
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  // the LUT fill comes AFTER the first stages are on their way: their DRAM latency hides behind it (a call of one
+  // 1080p frame is two steps per warp, so the fill and the first load are a third of its run time)
+  for (int i = threadIdx.x; i < entries * R; i += blockDim.x) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  __syncthreads();
   const uint32_t st0 = ring + lane * 4;
   for (unsigned kk = 0; kk < nsteps; kk += D) {
 #pragma unroll
@@ -817,11 +823,10 @@ __global__ void __launch_bounds__(1024, 1) k_decode_reg(const DecodeArgs p) {
   k.bias = pk(p.log_bias, p.log_bias);
 
   const unsigned g = blockIdx.x * (unsigned) p.lin_wpc + warp;
-  if (g >= (unsigned) p.lin_warps) return;
   const unsigned T = (unsigned) p.tiles_per_row, rows2 = (unsigned) p.rows2, drp = (unsigned) p.lin_drp;
   const unsigned rp0 = g / T, tile = g - rp0 * T;
-  if (rp0 >= rows2) return;
-  const unsigned nsteps = (rows2 - rp0 + drp - 1) / drp;
+  // (a warp without work still fills its share of the LUT and meets the CTA barrier below)
+  const unsigned nsteps = g < (unsigned) p.lin_warps && rp0 < rows2 ? (rows2 - rp0 + drp - 1) / drp : 0u;
   const uint8_t *yp = p.y + (long long) rp0 * 2 * p.py + (size_t) (tile * 32 + lane) * 4;
   const uint8_t *cp = p.c + (long long) rp0 * p.pc + (size_t) (tile * 32 + lane) * 4;
   const long long py = p.py, yinc = (long long) drp * 2 * p.py, cinc = (long long) drp * p.pc;
@@ -885,7 +890,25 @@ static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s
   a.lin_wpc = wpc;
   a.lin_warps = (int) (W / T * T);
   a.lin_drp = a.lin_warps / (int) T;
-  k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY><<<(unsigned) grid, wpc * 32, lut_bytes + (size_t) wpc * slice, s>>>(a), note_launch();
+  // Small calls (the few-replica LUT instantiations, RL2 < 5) are launched with programmatic stream serialization:
+  // back-to-back calls on one stream (the reference's one-frame-per-call pattern) overlap this launch's scheduling
+  // with the previous kernel's tail; the kernel waits (griddepcontrol.wait) before it touches global memory.
+  // BT709_PDL=0 disables it, BT709_PDL=all applies it to every k_decode_lin launch.
+  static const char *pdl_env = getenv("BT709_PDL");
+  const bool pdl = pdl_env ? (pdl_env[0] == 'a' || (pdl_env[0] != '0' && RL2 < 5)) : RL2 < 5;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned) grid);
+  cfg.blockDim = dim3((unsigned) wpc * 32);
+  cfg.dynamicSmemBytes = lut_bytes + (size_t) wpc * slice;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const cudaError_t le = cudaLaunchKernelEx(&cfg, k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY>, a);
+  note_launch();
+  if (le != cudaSuccess) return (int) le;
   return (int) cudaGetLastError();
 }
 

@@ -23,7 +23,7 @@
 
 namespace bt709 {
 
-size_t pair_layout_bytes(unsigned base, int cells, unsigned extra_bytes, int warps);  // bt709_rescale.cu
+size_t pair_layout_bytes(unsigned base, int cells, unsigned extra_bytes, int warps, int row_words);  // bt709_rescale.cu
 extern int g_dyn_smem_base;
 
 // CL2/RL2: decode LUT geometry (10, 3), or (-1, 5) = the encode LUT itself (Linear mode)
@@ -145,7 +145,7 @@ int launch_fused(const DecodeArgs &d0, const RescaleArgs &r0, uint8_t *scratch, 
   const bool linear = d.blog_lut && d.blog_cells > 0;  // Linear mode: the decode step function is the encode LUT
   if (!linear && d.cells_log2 != 10) return -1;
   const unsigned dec_bytes = linear ? 0u : ((1025u * 8u * 4u + 127u) & ~127u);
-  const size_t smem = pair_layout_bytes((unsigned) g_dyn_smem_base, r.enc_blog_cells, dec_bytes, kFusedWarps);
+  const size_t smem = pair_layout_bytes((unsigned) g_dyn_smem_base, r.enc_blog_cells, dec_bytes, kFusedWarps, kWalkRowInfo);
   if (smem > kMaxDynSmem) return -1;
   FusedArgs a{};
   a.bands = (r.oh + kWalkTH - 1) / kWalkTH;

@@ -1,6 +1,8 @@
 // bt709_pair.cuh — the paired-column pass-2 walker (tables + one warp tile), shared by k_rescale_pair
 // (bt709_rescale.cu) and the fused decode -> rescale kernel (bt709_fused.cu).
 #pragma once
+#include <type_traits>
+
 #include "bt709_device.cuh"
 
 namespace bt709 {
@@ -39,10 +41,20 @@ constexpr int kWalkRowInfo = (kWalkTH + 1) * 4;  // words of row info per warp (
 #ifndef BT709_PAIR_NP
 #define BT709_PAIR_NP 2
 #endif
+#ifndef BT709_PAIR_TH
+#define BT709_PAIR_TH 64
+#endif
 constexpr int kPairWarps = BT709_PAIR_WARPS;
+constexpr int kPairTH = BT709_PAIR_TH;        // output rows per warp tile of k_rescale_pair (the fused kernel's bands stay kWalkTH)
+constexpr int kPairRowInfo = (kPairTH + 1) * 4;
 constexpr int kPairPD = BT709_PAIR_PD;        // source rows fetched ahead of use by pair_tile (standalone kernel)
 constexpr int kPairNP = BT709_PAIR_NP;        // column pairs per thread on the opaque code: warp tile = 64 * kPairNP columns
 constexpr int kFusedWarps = 20, kFusedPD = 2;
+#ifdef BT709_NO_INNER
+constexpr bool kPairInner = false;
+#else
+constexpr bool kPairInner = true;  // pair_tile: separate code for warp tiles without clamped taps (see `fetch`)
+#endif
 
 struct PairCtx {
   uint32_t lin_lane, rows_base, enc_base;
@@ -59,7 +71,8 @@ struct H3 {
 //   [encode LUT, biased log cells: cell i replica r at word i*32 + r][pad][lin table at the next 64 KB boundary:
 //    word b*64 + r = sRGB byte b -> linear float, replica r; the upper 128 B of each 256-B entry are unused][row info]
 // extra_bytes: room the caller wants between the encode LUT and the pad (the fused kernel's decode LUT)
-__device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s_mem, uint32_t extra_bytes = 0) {  // row info: one slice per warp of the CTA
+__device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s_mem, uint32_t extra_bytes = 0,
+                                               int row_words = kWalkRowInfo) {  // row info: one slice of row_words per warp of the CTA
   const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_mem);
   const int nenc = p.enc_blog_cells << 5;
   const uint32_t extra_at = ((uint32_t) (nenc + 4) * 4u + 127u) & ~127u;
@@ -77,7 +90,7 @@ __device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   PairCtx c;
   c.lin_lane = (smem0 + pad) | (lane << 2);
-  c.rows_base = (uint32_t) __cvta_generic_to_shared(s_rows + warp * kWalkRowInfo);
+  c.rows_base = (uint32_t) __cvta_generic_to_shared(s_rows + warp * row_words);
   c.enc_base = *reinterpret_cast<volatile uint32_t *>(s_enc - 1) + (lane << 2);
   c.extra = smem0 + extra_at;
   c.clamp_lo = p.enc_blog_clamp_lo;
@@ -101,7 +114,7 @@ __device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s
 // opaque (the fused kernel: pass 1 without an alpha stream writes A = 255).
 // PD: source rows fetched ahead of use.  l2_policy (NC == false only): createpolicy handle for the tap loads (the fused
 // kernel keeps its slice resident in L2 with evict_last).
-template <bool ALPHA, bool NC = true, int NP = 1, bool SPEC = true, int PD = kPairPD>
+template <bool ALPHA, bool NC = true, int NP = 1, bool SPEC = true, int PD = kPairPD, int TH = kWalkTH, bool INNER_PATH = kPairInner>
 __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c, const uint8_t *src_frame, unsigned pi,
                                           uint8_t *dst_frame, int ox0, int oy0, int lane, unsigned long long l2_policy = 0) {
   uint32_t lin_lane = c.lin_lane, enc_base = c.enc_base;
@@ -133,14 +146,14 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
 
   __syncwarp();
 #pragma unroll
-  for (int k = 0; k < kWalkTH / 32; k++) {
+  for (int k = 0; k < TH / 32; k++) {
     const int r = k * 32 + lane, oy = oy0 + r;
     const float sy = __fadd_rn(__fmul_rn(__fadd_rn((float) oy, 0.5f), p.scale_y), -0.5f);
     const float fy0 = floorf(sy);
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(rows_base + r * 16), "r"(__float_as_uint(__fsub_rn(sy, fy0))),
                  "r"(oy < p.oh ? (uint32_t) (int) fy0 : 0x7fffffffu) : "memory");
   }
-  if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1,%1};" ::"r"(rows_base + kWalkTH * 16), "r"(0x7fffffffu) : "memory");
+  if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1,%1};" ::"r"(rows_base + TH * 16), "r"(0x7fffffffu) : "memory");
   __syncwarp();
 
   const int ylast = p.ih - 1, xlast = p.iw - 1;
@@ -173,33 +186,49 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
 
   uint32_t acc = 0xFFFFFFFFu;  // AND of every tap word: byte 3 stays 255 while the tile is opaque
   struct Taps { uint32_t w0, w1, w2; };
-  auto fetch = [&](int row, Taps (&t)[NP]) {
+  // INNER (a compile-time flag, see below): no tap of this warp tile is clamped at the left or right image edge, so
+  // the three texels of every pair are adjacent words: immediate offsets instead of two 64-bit adds per load
+  auto fetch = [&](int row, Taps (&t)[NP], auto inner) {
+    constexpr bool INNER = decltype(inner)::value;
     const unsigned step = (unsigned) row < (unsigned) ylast ? pi : 0u;
 #pragma unroll
     for (int q = 0; q < NP; q++) {
+      const uint8_t *f1 = INNER ? fp[q] + 4 : fp[q] + d1[q], *f2 = INNER ? fp[q] + 8 : fp[q] + d2[q];
       if (NC) {
         t[q].w0 = __ldg(reinterpret_cast<const uint32_t *>(fp[q]));
-        t[q].w1 = __ldg(reinterpret_cast<const uint32_t *>(fp[q] + d1[q]));
-        t[q].w2 = __ldg(reinterpret_cast<const uint32_t *>(fp[q] + d2[q]));
+        t[q].w1 = __ldg(reinterpret_cast<const uint32_t *>(f1));
+        t[q].w2 = __ldg(reinterpret_cast<const uint32_t *>(f2));
       } else {
         asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t[q].w0) : "l"(fp[q]), "l"(l2_policy) : "memory");
-        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t[q].w1) : "l"(fp[q] + d1[q]), "l"(l2_policy) : "memory");
-        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t[q].w2) : "l"(fp[q] + d2[q]), "l"(l2_policy) : "memory");
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t[q].w1) : "l"(f1), "l"(l2_policy) : "memory");
+        asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(t[q].w2) : "l"(f2), "l"(l2_policy) : "memory");
       }
       fp[q] += step;
     }
   };
   auto blend = [&](const Taps &t, int q) -> H3 {
     const uint32_t w0 = t.w0, w1 = t.w1, w2 = t.w2;
-    const uint32_t u0 = bsel[q] ? w1 : w0, u1 = bsel[q] ? w2 : w1;  // column b's taps
+    const uint32_t u0 = bsel[q] ? w1 : w0, u1 = bsel[q] ? w2 : w1;  // column b's taps (alpha; colour with BT709_PAIR_TAPS12)
     if (SPEC) {
       acc = acc & w0 & w1;
       acc &= w2;
     }
     H3 h;
+#ifdef BT709_PAIR_TAPS12
     h.r = lerp(pk(lin_of(w0, 0x7624), lin_of(u0, 0x7624)), pk(lin_of(w1, 0x7624), lin_of(u1, 0x7624)), fx2[q]);
     h.g = lerp(pk(lin_of(w0, 0x7614), lin_of(u0, 0x7614)), pk(lin_of(w1, 0x7614), lin_of(u1, 0x7614)), fx2[q]);
     h.b = lerp(pk(lin_of(w0, 0x7604), lin_of(u0, 0x7604)), pk(lin_of(w1, 0x7604), lin_of(u1, 0x7604)), fx2[q]);
+#else
+    // each of the three texels is converted once (9 table reads per pair and row instead of 12: the shared-memory pipe
+    // is as busy as the issue slots in this kernel), column b's taps are selected as floats
+    auto chan = [&](uint32_t sel) -> f32x2 {
+      const float l0 = lin_of(w0, sel), l1 = lin_of(w1, sel), l2 = lin_of(w2, sel);
+      return lerp(pk(l0, bsel[q] ? l1 : l0), pk(l1, bsel[q] ? l2 : l1), fx2[q]);
+    };
+    h.r = chan(0x7624);
+    h.g = chan(0x7614);
+    h.b = chan(0x7604);
+#endif
     if (ALPHA) {  // alpha is linear: byte * (1/255), exactly as the oracle's tap
       const f32x2 a0 = mul2(add2(pku(magic_byte<3>(w0), magic_byte<3>(u0)), c.nmagic2), c.inv255_2);
       const f32x2 a1 = mul2(add2(pku(magic_byte<3>(w1), magic_byte<3>(u1)), c.nmagic2), c.inv255_2);
@@ -208,6 +237,12 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
     return h;
   };
 
+  bool inner_ok = true;
+#pragma unroll
+  for (int q = 0; q < NP; q++) inner_ok = inner_ok && d1[q] == 4u && d2[q] == 8u;
+  inner_ok = __all_sync(0xffffffffu, inner_ok);  // warp-uniform: one of the two instantiations below runs
+
+  auto walk = [&](auto inner) {
   uint32_t ip = rows_base;
   uint32_t info_fy, info_y;
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(info_fy), "=r"(info_y) : "r"(ip));
@@ -215,9 +250,9 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
   Taps qq[PD][NP], first[NP];
 #pragma unroll
   for (int q = 0; q < NP; q++) fp[q] = ptr_mad(fp[q], (unsigned) max(y, 0), pi);
-  fetch(y, first);
+  fetch(y, first, inner);
 #pragma unroll
-  for (int j = 0; j < PD; j++) fetch(y + 1 + j, qq[j]);
+  for (int j = 0; j < PD; j++) fetch(y + 1 + j, qq[j], inner);
   H3 H[2][NP];
 #pragma unroll
   for (int q = 0; q < NP; q++) H[0][q] = blend(first[q], q);
@@ -227,7 +262,7 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
     for (int j = 0; j < 2 * PD; j++) {
 #pragma unroll
       for (int q = 0; q < NP; q++) H[(j + 1) & 1][q] = blend(qq[j % PD][q], q);
-      fetch(y + 1 + PD, qq[j % PD]);
+      fetch(y + 1 + PD, qq[j % PD], inner);
       while ((int) info_y <= y) {
         dp += po;
         const float fy = __uint_as_float(info_fy);
@@ -251,7 +286,8 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
             wa = __byte_perm(__byte_perm(ba, ga, 0x0073), ra, 0x7710) | 0xFF000000u;
             wb = __byte_perm(__byte_perm(bb, gb, 0x0073), rb, 0x7710) | 0xFF000000u;
           }
-          if (live[q]) st_stream_u64(dp + q * 256, make_uint2(wa, wb));  // streaming: the output is never read back
+          // (an inner tile has no pair beyond the right edge: such a pair's taps would all be clamped)
+          if (decltype(inner)::value || live[q]) st_stream_u64(dp + q * 256, make_uint2(wa, wb));  // streaming: never read back
         }
         ip += 16;
         asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(info_fy), "=r"(info_y) : "r"(ip));
@@ -260,6 +296,9 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
       if (info_y == 0x7fffffffu) { done = true; break; }
     }
   }
+  };
+  if (INNER_PATH && inner_ok) walk(std::true_type{});
+  else walk(std::false_type{});
   return __all_sync(0xffffffffu, (acc >> 24) == 0xFFu);
 }
 

@@ -456,32 +456,53 @@ __global__ void __launch_bounds__(kWalk2Warps * 32, 1) k_rescale_cols2(const Res
 
 __global__ void __launch_bounds__(kPairWarps * 32, 1) k_rescale_pair(const RescaleArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
-  const PairCtx c = pair_tables(p, s_mem);
+  const PairCtx c = pair_tables(p, s_mem, 0, kPairRowInfo);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int TW = 64 * kPairNP;  // tile width
-  const int tiles_x = (p.ow + TW - 1) / TW, tiles_y = (p.oh + kWalkTH - 1) / kWalkTH;
+  const int tiles_x = (p.ow + TW - 1) / TW, tiles_y = (p.oh + kPairTH - 1) / kPairTH;
   const unsigned tiles_per_frame = tiles_x * tiles_y;
   const unsigned tiles = (unsigned) p.nframes * tiles_per_frame;
   bool with_alpha = false;  // warp-uniform: the code this warp tries first on its next tile
+  // Tile order: every tile that is not in the first or last tile column first, those two columns at the end.  The
+  // walker has separate code for tiles without clamped taps (pair_tile: INNER), each variant a ~20 KB loop; with edge
+  // tiles sprinkled through the order, one or two warps of every CTA sit in the other variant at any time and the
+  // instruction cache thrashes (measured: 288 against 327 Gpix/s).  (The variant itself is still chosen by a vote on
+  // the real tap offsets: the order only decides WHEN a warp meets an edge tile.)
+  const unsigned inner_x = tiles_x > 2 ? (unsigned) tiles_x - 2u : 0u, edge_x = (unsigned) tiles_x - inner_x;
+  const unsigned n_inner = (unsigned) p.nframes * (unsigned) tiles_y * inner_x;
   for (unsigned t = blockIdx.x * kPairWarps + warp; t < tiles; t += gridDim.x * kPairWarps) {
-    const unsigned f = t / tiles_per_frame, tr = t - f * tiles_per_frame;
-    const int ty = tr / tiles_x, tx = tr - ty * tiles_x;
+    unsigned f;
+    int ty, tx;
+    if (t < n_inner) {
+      const unsigned per = (unsigned) tiles_y * inner_x;
+      f = t / per;
+      const unsigned tr = t - f * per;
+      ty = (int) (tr / inner_x);
+      tx = (int) (tr - (unsigned) ty * inner_x) + 1;
+    } else {
+      const unsigned e = t - n_inner, per = (unsigned) tiles_y * edge_x;
+      f = e / per;
+      const unsigned tr = e - f * per;
+      ty = (int) (tr / edge_x);
+      const unsigned k = tr - (unsigned) ty * edge_x;
+      tx = inner_x ? (k ? tiles_x - 1 : 0) : (int) k;
+    }
     const uint8_t *src = p.in + (long long) f * p.si;
     uint8_t *dst = p.out + (long long) f * p.so;
     const unsigned pi = (unsigned) p.pi;
-    const int ox0 = tx * TW, oy0 = ty * kWalkTH;
+    const int ox0 = tx * TW, oy0 = ty * kPairTH;
     // the alpha code runs one pair per thread (a 64-column half tile at a time) to stay within the register budget
     auto alpha_tile = [&]() -> bool {
       bool opaque = true;
 #pragma unroll 1
       for (int q = 0; q < kPairNP; q++)
-        if (ox0 + q * 64 < p.ow) opaque = pair_tile<true, true, 1, true, kPairPD>(p, c, src, pi, dst, ox0 + q * 64, oy0, lane) && opaque;
+        if (ox0 + q * 64 < p.ow) opaque = pair_tile<true, true, 1, true, kPairPD, kPairTH>(p, c, src, pi, dst, ox0 + q * 64, oy0, lane) && opaque;
       return opaque;
     };
     if (p.known_opaque) {  // the source was written by pass 1 without an alpha stream: nothing to watch for
-      pair_tile<false, true, kPairNP, false, kPairPD>(p, c, src, pi, dst, ox0, oy0, lane);
+      pair_tile<false, true, kPairNP, false, kPairPD, kPairTH>(p, c, src, pi, dst, ox0, oy0, lane);
     } else if (!with_alpha) {
-      if (!pair_tile<false, true, kPairNP, true, kPairPD>(p, c, src, pi, dst, ox0, oy0, lane)) {  // a tap with A != 255: redo with alpha
+      if (!pair_tile<false, true, kPairNP, true, kPairPD, kPairTH>(p, c, src, pi, dst, ox0, oy0, lane)) {  // a tap with A != 255: redo with alpha
         alpha_tile();
         with_alpha = true;
       }
@@ -505,10 +526,10 @@ static size_t elog_layout_bytes(unsigned base, int cells, int warps) {
 }
 
 // dynamic bytes k_rescale_pair needs: [LUT, 32 replicas][pad to 64 KB][table 64 KB][row info]
-size_t pair_layout_bytes(unsigned base, int cells, unsigned extra_bytes, int warps) {
+size_t pair_layout_bytes(unsigned base, int cells, unsigned extra_bytes, int warps, int row_words) {
   const unsigned head = ((((unsigned) cells * 32u + 4u) * 4u + 127u) & ~127u) + extra_bytes;
   const unsigned pad = head + ((0x10000u - ((base + head) & 0xFFFFu)) & 0xFFFFu);
-  return (size_t) pad + 65536u + (size_t) warps * kWalkRowInfo * 4u;
+  return (size_t) pad + 65536u + (size_t) warps * row_words * 4u;
 }
 
 static size_t walk_smem_bytes(int enc_cells_log2, int rep_log2) {  // 64 KB of alignment slack in front of the table
@@ -545,12 +566,12 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
       // (even width and 8-byte aligned rows: every column pair is stored with one 8-byte store)
       const bool pair_ok = (a.ow % 2 == 0) && aligned(a.out, 8) && aligned(a.po, 8) && aligned(a.so, 8);
       if (a.iw <= a.ow && pair_ok && !no_pair && !no_cols2 && b.enc_blog_lut && g_dyn_smem_base >= 0 &&
-          pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0, kPairWarps) <= kMaxDynSmem) {
+          pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0, kPairWarps, kPairRowInfo) <= kMaxDynSmem) {
         // horizontal scale <= 1: paired columns, opaque speculation, conflict-free encode LUT (k_rescale_pair)
-        const long long tiles64 = (long long) ((a.ow + 64 * kPairNP - 1) / (64 * kPairNP)) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
+        const long long tiles64 = (long long) ((a.ow + 64 * kPairNP - 1) / (64 * kPairNP)) * ((a.oh + kPairTH - 1) / kPairTH) * b.nframes;
         const long long ctas2 = (tiles64 + kPairWarps - 1) / kPairWarps;
         const unsigned g2 = (unsigned) (ctas2 < (long long) sm_count ? ctas2 : (long long) sm_count);
-        k_rescale_pair<<<g2, kPairWarps * 32, pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0, kPairWarps), st>>>(b), note_launch();
+        k_rescale_pair<<<g2, kPairWarps * 32, pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0, kPairWarps, kPairRowInfo), st>>>(b), note_launch();
       } else if (a.iw <= a.ow && !no_cols2 && (elog || smem_u <= kMaxDynSmem)) {
         // horizontal scale <= 1: two adjacent columns per thread share their middle texel
         const long long tiles64 = (long long) ((a.ow + 63) / 64) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
