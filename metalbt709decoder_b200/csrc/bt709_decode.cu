@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_fast(const DecodeArgs p) 
   extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = 1 << CL2, R = 1 << RL2;
   const int entries = CL2 ? N + 1 : p.log_cells;  // CL2 == 0: log-spaced cell LUT (bt709_tables.h: LogLut)
-  for (int i = threadIdx.x; i < entries * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  fill_replicated<RL2>(s_lut, R, p.lut, entries);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
   const int entries = CL2 ? N + 1 : p.log_cells;  // CL2 == 0: log-spaced cell LUT
   const uint32_t kLutBytes = (uint32_t) entries * R * 4;
   constexpr uint32_t kStage = ALPHA ? 640 : 384;  // Y0 | Y1 | CbCr (| A0 | A1), 128 B each
-  for (int i = threadIdx.x; i < entries * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  fill_replicated<RL2>(s_lut, R, p.lut, entries);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -333,8 +333,8 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   // Programmatic dependent launch (small calls, launch_decode_lin1): let the next launch of the stream be scheduled
   // now, and wait here until the previous kernel of the stream has completed and its writes are visible.  Both are
   // no-ops for a launch without the attribute.  Nothing above this line touches global memory.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  asm volatile("griddepcontrol.wait;" ::: "memory");
+  pdl_launch_dependents();
+  pdl_wait();
 
   const int lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   }
   // the LUT fill comes AFTER the first stages are on their way: their DRAM latency hides behind it (a call of one
   // 1080p frame is two steps per warp, so the fill and the first load are a third of its run time)
-  for (int i = threadIdx.x; i < entries * R; i += blockDim.x) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  fill_replicated<RL2>(s_lut, R, p.lut, entries);
   __syncthreads();
   const uint32_t st0 = ring + lane * 4;
   for (unsigned kk = 0; kk < nsteps; kk += D) {
@@ -497,7 +497,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_bulk(const DecodeArgs p) 
   extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = 1 << CL2, R = 1 << RL2;
   constexpr uint32_t kLutBytes = (uint32_t) (N + 1) * R * 4;
-  for (int i = threadIdx.x; i < (N + 1) * R; i += THREADS) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  fill_replicated<RL2>(s_lut, R, p.lut, N + 1);
 
   const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_lut);
   const uint32_t ring0 = smem0 + kLutBytes;
@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(1024, 1) k_decode_reg(const DecodeArgs p) {
   extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = CL2 > 0 ? 1 << CL2 : 1, R = 1 << RL2;
   const int entries = CL2 > 0 ? N + 1 : p.log_cells;
-  for (int i = threadIdx.x; i < entries * R; i += blockDim.x) s_lut[i] = __ldg(&p.lut[i >> RL2]);
+  fill_replicated<RL2>(s_lut, R, p.lut, entries);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
@@ -893,20 +893,9 @@ static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s
   // Small calls (the few-replica LUT instantiations, RL2 < 5) are launched with programmatic stream serialization:
   // back-to-back calls on one stream (the reference's one-frame-per-call pattern) overlap this launch's scheduling
   // with the previous kernel's tail; the kernel waits (griddepcontrol.wait) before it touches global memory.
-  // BT709_PDL=0 disables it, BT709_PDL=all applies it to every k_decode_lin launch.
-  static const char *pdl_env = getenv("BT709_PDL");
-  const bool pdl = pdl_env ? (pdl_env[0] == 'a' || (pdl_env[0] != '0' && RL2 < 5)) : RL2 < 5;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned) grid);
-  cfg.blockDim = dim3((unsigned) wpc * 32);
-  cfg.dynamicSmemBytes = lut_bytes + (size_t) wpc * slice;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl ? 1 : 0;
-  const cudaError_t le = cudaLaunchKernelEx(&cfg, k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY>, a);
+  // BT709_PDL=0 disables it, BT709_PDL=all applies it to every launch that supports it (pdl_enabled).
+  const cudaError_t le = launch_pdl(k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY>, (unsigned) grid, (unsigned) wpc * 32,
+                                    lut_bytes + (size_t) wpc * slice, s, pdl_enabled(RL2 < 5), a);
   note_launch();
   if (le != cudaSuccess) return (int) le;
   return (int) cudaGetLastError();

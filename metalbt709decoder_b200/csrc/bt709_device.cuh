@@ -89,6 +89,37 @@ __device__ __forceinline__ uint32_t lut_code(const uint32_t *lut, float x, float
   return (lut[idx] + __float_as_uint(xc)) >> 24;
 }
 
+// ------------------------------------------------------------------ replicated table fill
+// Entry e of src (n entries) -> R = 1 << RL2 consecutive words at dst + e * stride_words (stride_words >= R, dst and
+// the stride 16-byte aligned), R >= 4.  A warp loads 32 entries with ONE coalesced read and hands them round by shuffle;
+// R / 4 lanes write one entry's replicas with 16-byte stores, so a store instruction covers 512 contiguous bytes
+// (stride_words == R) without bank conflicts.  The old loop `dst[i] = __ldg(&src[i >> RL2])` read every entry R times:
+// R * n / threads dependent L2 round trips per thread, 2-4 us per launch - a third of a one-frame call.
+template <int RL2>
+__device__ __forceinline__ void fill_replicated(uint32_t *dst, int stride_words, const uint32_t *src, int n) {
+  static_assert(RL2 >= 2 && RL2 <= 5, "4 to 32 replicas");
+  constexpr int LPE = 1 << (RL2 - 2);   // lanes per entry (16 bytes each)
+  constexpr int EPI = 32 / LPE;         // entries per store instruction
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int base = warp * 32; base < n; base += nwarps * 32) {
+    const uint32_t mine = base + lane < n ? __ldg(src + base + lane) : 0u;
+#pragma unroll
+    for (int j = 0; j < LPE; j++) {
+      const int sub = j * EPI + lane / LPE;  // entry of the block this lane stores in round j
+      const uint32_t v = __shfl_sync(0xffffffffu, mine, sub);
+      if (base + sub < n)
+        *reinterpret_cast<uint4 *>(dst + (size_t) (base + sub) * stride_words + (lane % LPE) * 4) = make_uint4(v, v, v, v);
+    }
+  }
+}
+
+// Programmatic dependent launch (kernels launched with cudaLaunchAttributeProgrammaticStreamSerialization, see
+// launch_pdl): let the next launch of the stream be scheduled / wait until the previous kernel of the stream has
+// completed and its writes are visible.  Both are no-ops in a launch without the attribute.  A kernel must not touch
+// global memory other than its constant tables before pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ------------------------------------------------------------------ packed float32 pairs
 // Blackwell packed instructions (add/mul/fma .f32x2 -> FADD2/FMUL2/FFMA2): identical IEEE results per
 // lane, half the issue slots.  NOTE: ptxas contracts a packed mul.rn.f32x2 feeding an add.rn.f32x2
@@ -149,6 +180,31 @@ __device__ __forceinline__ uint32_t magic_byte(uint32_t word) {  // bits of the 
 }
 
 // ------------------------------------------------------------------ host-side helpers
+// <<<grid, block, smem, stream>>> with or without programmatic stream serialization (small calls: the launch overlaps
+// the tail of the previous kernel of the stream; the kernel itself calls pdl_wait() before it touches its inputs)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t s, bool pdl,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+// BT709_PDL=0: never; BT709_PDL=all: every launch that supports it; default: small calls only
+static inline bool pdl_enabled(bool small_call) {
+  static const char *env = getenv("BT709_PDL");
+  if (!env) return small_call;
+  if (env[0] == 'a') return true;
+  return env[0] != '0' && small_call;
+}
+
 static inline bool aligned(const void *p, size_t a) { return ((uintptr_t) p & (a - 1)) == 0; }
 static inline bool aligned(long long v, size_t a) { return ((unsigned long long) v & (a - 1)) == 0; }
 

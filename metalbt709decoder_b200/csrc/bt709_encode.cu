@@ -137,14 +137,18 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   float2 *s_tab = reinterpret_cast<float2 *>(s_mem);
   uint32_t *s_olut = s_mem + 256 * 64;
   const int nl = (1 << p.out_cells_log2) + 1;
-  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) {
-    const int b = i >> 5;
-    s_tab[i] = make_float2(__ldg(&p.lin256[b]), __ldg(&p.compn256[b]));
+  pdl_launch_dependents();
+  // every table entry is read from global memory once and its replicas are written with 16-byte stores (the old
+  // loops read an entry once per replica: ~10 dependent L2 round trips per thread, a third of a one-frame call)
+  for (int b = threadIdx.x >> 4; b < 256; b += blockDim.x >> 4) {  // 16 lanes per entry: 32 x {lin, compn} = 256 bytes
+    const float l = __ldg(&p.lin256[b]), cn = __ldg(&p.compn256[b]);
+    reinterpret_cast<float4 *>(s_tab + b * 32)[threadIdx.x & 15] = make_float4(l, cn, l, cn);
   }
   // chroma cell LUT replicated 8x (entry i replica r at word i*8 + r): random means otherwise
   // cost ~3 wavefronts per lookup and the kernel is bound by shared-memory bandwidth
-  for (int i = threadIdx.x; i < nl * 8; i += blockDim.x) s_olut[i] = __ldg(&p.out_lut[i >> 3]);
+  fill_replicated<3>(s_olut, 8, p.out_lut, nl);
   __syncthreads();
+  pdl_wait();  // small calls are launched with programmatic stream serialization: the tables above are constant
 
   const int lane = threadIdx.x & 31;
   const unsigned warp = threadIdx.x >> 5;
@@ -340,10 +344,13 @@ static int launch_encode_fast1(const EncodeArgs &a0, int sm_count, cudaStream_t 
   // The looping instantiation is also valid for narrower rows (its loop runs once) and its code schedule measured
   // faster when all 32 warps have a tile (2048 wide: 905 vs 883 Gpix/s), slower with 30 (1920 wide: 881 vs 916).
   const bool wide = a.tiles_per_row > wpc || wpc % a.tiles_per_row == 0;
+  // calls of a few steps per warp (one or two frames) are launched with programmatic stream serialization
+  const bool pdl = pdl_enabled((unsigned long long) total_rp <= 4ull * a.step_rp);
+  cudaError_t le = cudaSuccess;
 #define BT709_ENC_LAUNCH(W, F)                                                      \
   do {                                                                              \
-    if (wide) k_encode_fast<W, F, true><<<grid, 1024, smem, s>>>(a), note_launch();                \
-    else k_encode_fast<W, F, false><<<grid, 1024, smem, s>>>(a), note_launch();                    \
+    if (wide) le = launch_pdl(k_encode_fast<W, F, true>, grid, 1024, smem, s, pdl, a), note_launch();   \
+    else le = launch_pdl(k_encode_fast<W, F, false>, grid, 1024, smem, s, pdl, a), note_launch();        \
   } while (0)
   if (wrap) {
     if (full) BT709_ENC_LAUNCH(true, true); else BT709_ENC_LAUNCH(true, false);
@@ -351,6 +358,7 @@ static int launch_encode_fast1(const EncodeArgs &a0, int sm_count, cudaStream_t 
     if (full) BT709_ENC_LAUNCH(false, true); else BT709_ENC_LAUNCH(false, false);
   }
 #undef BT709_ENC_LAUNCH
+  if (le != cudaSuccess) return (int) le;
   return (int) cudaGetLastError();
 }
 

@@ -40,7 +40,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(const FusedArgs a
   if (CL2 > 0) {
     const uint32_t smem0 = (uint32_t) __cvta_generic_to_shared(s_mem);
     uint32_t *s_dec = s_mem + ((c.extra - smem0) >> 2);
-    for (int i = threadIdx.x; i < (N + 1) * R; i += blockDim.x) s_dec[i] = __ldg(&d.lut[i >> RL2]);
+    fill_replicated<RL2>(s_dec, R, d.lut, N + 1);
     __syncthreads();
     sbase = c.extra + ((lane & (R - 1)) << 2) - (0x4B000000u << (2 + RL2));
   } else {

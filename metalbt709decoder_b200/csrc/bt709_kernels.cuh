@@ -75,6 +75,7 @@ struct RescaleArgs {
   unsigned enc_blog_first;
   float one;  // 1.0f, deliberately a runtime value (blocks FFMA2 contraction, see k_rescale_cols)
   int known_opaque;  // the caller guarantees A = 255 everywhere (pass 1 without an alpha stream wrote the source)
+  int pair_th;       // k_rescale_pair: output rows per warp tile (launcher: kPairTH, less for calls of a few frames)
 };
 
 struct EncodeArgs {

@@ -81,8 +81,8 @@ __device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s
   float *s_lin = reinterpret_cast<float *>(s_mem + (pad >> 2));
   uint32_t *s_rows = s_mem + (pad >> 2) + 256 * 64;
   uint32_t *s_enc = s_mem + 4;
-  for (int i = threadIdx.x; i < 256 * 32; i += blockDim.x) s_lin[(i >> 5) * 64 + (i & 31)] = __ldg(&p.lin256[i >> 5]);
-  for (int i = threadIdx.x; i < nenc; i += blockDim.x) s_enc[i] = __ldg(&p.enc_blog_lut[i >> 5]);
+  fill_replicated<5>(reinterpret_cast<uint32_t *>(s_lin), 64, reinterpret_cast<const uint32_t *>(p.lin256), 256);
+  fill_replicated<5>(s_enc, 32, p.enc_blog_lut, p.enc_blog_cells);
   // (index register << 7) + enc_base, the index register holding first + cell: the bias goes through shared memory so
   // that ptxas sees an opaque register and emits one LEA per lookup
   if (threadIdx.x == 0) s_enc[-1] = (uint32_t) __cvta_generic_to_shared(s_enc) - (p.enc_blog_first << 7);
@@ -102,7 +102,7 @@ __device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s
   return c;
 }
 
-// One warp tile (64 * NP output columns x kWalkTH output rows).  Returns true when every tap word it fetched had A = 255.
+// One warp tile (64 * NP output columns x th output rows).  Returns true when every tap word it fetched had A = 255.
 // src_frame / dst_frame: row 0 of the source and destination frame; pi: source pitch in bytes; oy0: first output row;
 // ox0: first output column of the tile (64 * NP columns wide).
 // NC: the source is read-only for the whole kernel (ld.global.nc); the fused kernel reads rows its own CTA has just
@@ -114,9 +114,10 @@ __device__ __forceinline__ PairCtx pair_tables(const RescaleArgs &p, uint32_t *s
 // opaque (the fused kernel: pass 1 without an alpha stream writes A = 255).
 // PD: source rows fetched ahead of use.  l2_policy (NC == false only): createpolicy handle for the tap loads (the fused
 // kernel keeps its slice resident in L2 with evict_last).
-template <bool ALPHA, bool NC = true, int NP = 1, bool SPEC = true, int PD = kPairPD, int TH = kWalkTH, bool INNER_PATH = kPairInner>
+template <bool ALPHA, bool NC = true, int NP = 1, bool SPEC = true, int PD = kPairPD, bool INNER_PATH = kPairInner>
 __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c, const uint8_t *src_frame, unsigned pi,
-                                          uint8_t *dst_frame, int ox0, int oy0, int lane, unsigned long long l2_policy = 0) {
+                                          uint8_t *dst_frame, int ox0, int oy0, int lane, unsigned long long l2_policy = 0,
+                                          int th = kWalkTH) {
   uint32_t lin_lane = c.lin_lane, enc_base = c.enc_base;
   const uint32_t rows_base = c.rows_base;
   asm volatile("" : "+r"(lin_lane), "+r"(enc_base));  // keep them in registers (ptxas rebuilt them every source row)
@@ -145,15 +146,16 @@ __device__ __forceinline__ bool pair_tile(const RescaleArgs &p, const PairCtx &c
   };
 
   __syncwarp();
-#pragma unroll
-  for (int k = 0; k < TH / 32; k++) {
-    const int r = k * 32 + lane, oy = oy0 + r;
+  // th: output rows of this tile (<= the row-info slice the caller sized, a run-time value: small calls use
+  // shorter tiles so that every warp of the grid has one)
+  for (int r = lane; r < th; r += 32) {
+    const int oy = oy0 + r;
     const float sy = __fadd_rn(__fmul_rn(__fadd_rn((float) oy, 0.5f), p.scale_y), -0.5f);
     const float fy0 = floorf(sy);
     asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(rows_base + r * 16), "r"(__float_as_uint(__fsub_rn(sy, fy0))),
                  "r"(oy < p.oh ? (uint32_t) (int) fy0 : 0x7fffffffu) : "memory");
   }
-  if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1,%1};" ::"r"(rows_base + TH * 16), "r"(0x7fffffffu) : "memory");
+  if (lane == 0) asm volatile("st.shared.v2.u32 [%0], {%1,%1};" ::"r"(rows_base + th * 16), "r"(0x7fffffffu) : "memory");
   __syncwarp();
 
   const int ylast = p.ih - 1, xlast = p.iw - 1;

@@ -456,10 +456,13 @@ __global__ void __launch_bounds__(kWalk2Warps * 32, 1) k_rescale_cols2(const Res
 
 __global__ void __launch_bounds__(kPairWarps * 32, 1) k_rescale_pair(const RescaleArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
+  pdl_launch_dependents();
   const PairCtx c = pair_tables(p, s_mem, 0, kPairRowInfo);
+  pdl_wait();  // (calls of a few frames are launched with programmatic stream serialization; the tables are constant)
+  const int th = p.pair_th;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int TW = 64 * kPairNP;  // tile width
-  const int tiles_x = (p.ow + TW - 1) / TW, tiles_y = (p.oh + kPairTH - 1) / kPairTH;
+  const int tiles_x = (p.ow + TW - 1) / TW, tiles_y = (p.oh + th - 1) / th;
   const unsigned tiles_per_frame = tiles_x * tiles_y;
   const unsigned tiles = (unsigned) p.nframes * tiles_per_frame;
   bool with_alpha = false;  // warp-uniform: the code this warp tries first on its next tile
@@ -470,7 +473,8 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) k_rescale_pair(const Resca
   // the real tap offsets: the order only decides WHEN a warp meets an edge tile.)
   const unsigned inner_x = tiles_x > 2 ? (unsigned) tiles_x - 2u : 0u, edge_x = (unsigned) tiles_x - inner_x;
   const unsigned n_inner = (unsigned) p.nframes * (unsigned) tiles_y * inner_x;
-  for (unsigned t = blockIdx.x * kPairWarps + warp; t < tiles; t += gridDim.x * kPairWarps) {
+  // (tile t goes to CTA t % grid: a call with fewer tiles than warps still uses every SM)
+  for (unsigned t = blockIdx.x + gridDim.x * warp; t < tiles; t += gridDim.x * kPairWarps) {
     unsigned f;
     int ty, tx;
     if (t < n_inner) {
@@ -490,19 +494,19 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) k_rescale_pair(const Resca
     const uint8_t *src = p.in + (long long) f * p.si;
     uint8_t *dst = p.out + (long long) f * p.so;
     const unsigned pi = (unsigned) p.pi;
-    const int ox0 = tx * TW, oy0 = ty * kPairTH;
+    const int ox0 = tx * TW, oy0 = ty * th;
     // the alpha code runs one pair per thread (a 64-column half tile at a time) to stay within the register budget
     auto alpha_tile = [&]() -> bool {
       bool opaque = true;
 #pragma unroll 1
       for (int q = 0; q < kPairNP; q++)
-        if (ox0 + q * 64 < p.ow) opaque = pair_tile<true, true, 1, true, kPairPD, kPairTH>(p, c, src, pi, dst, ox0 + q * 64, oy0, lane) && opaque;
+        if (ox0 + q * 64 < p.ow) opaque = pair_tile<true, true, 1, true, kPairPD>(p, c, src, pi, dst, ox0 + q * 64, oy0, lane, 0ull, th) && opaque;
       return opaque;
     };
     if (p.known_opaque) {  // the source was written by pass 1 without an alpha stream: nothing to watch for
-      pair_tile<false, true, kPairNP, false, kPairPD, kPairTH>(p, c, src, pi, dst, ox0, oy0, lane);
+      pair_tile<false, true, kPairNP, false, kPairPD>(p, c, src, pi, dst, ox0, oy0, lane, 0ull, th);
     } else if (!with_alpha) {
-      if (!pair_tile<false, true, kPairNP, true, kPairPD, kPairTH>(p, c, src, pi, dst, ox0, oy0, lane)) {  // a tap with A != 255: redo with alpha
+      if (!pair_tile<false, true, kPairNP, true, kPairPD>(p, c, src, pi, dst, ox0, oy0, lane, 0ull, th)) {  // a tap with A != 255: redo with alpha
         alpha_tile();
         with_alpha = true;
       }
@@ -568,10 +572,20 @@ int launch_rescale(const RescaleArgs &a, int sm_count, void *stream) {
       if (a.iw <= a.ow && pair_ok && !no_pair && !no_cols2 && b.enc_blog_lut && g_dyn_smem_base >= 0 &&
           pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0, kPairWarps, kPairRowInfo) <= kMaxDynSmem) {
         // horizontal scale <= 1: paired columns, opaque speculation, conflict-free encode LUT (k_rescale_pair)
-        const long long tiles64 = (long long) ((a.ow + 64 * kPairNP - 1) / (64 * kPairNP)) * ((a.oh + kPairTH - 1) / kPairTH) * b.nframes;
-        const long long ctas2 = (tiles64 + kPairWarps - 1) / kPairWarps;
-        const unsigned g2 = (unsigned) (ctas2 < (long long) sm_count ? ctas2 : (long long) sm_count);
-        k_rescale_pair<<<g2, kPairWarps * 32, pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0, kPairWarps, kPairRowInfo), st>>>(b), note_launch();
+        // tile height: kPairTH rows, halved while the call has fewer tiles than the grid has warps (one 1080p -> 1440p
+        // frame: 460 tiles of 64 rows for 2368 warps; 1800 of 16 rows) - shorter tiles cost a few source rows of halo
+        const long long tiles_x = (a.ow + 64 * kPairNP - 1) / (64 * kPairNP);
+        int th = kPairTH;
+        while (th > 16 && tiles_x * ((a.oh + th - 1) / th) * b.nframes < (long long) sm_count * kPairWarps) th >>= 1;
+        b.pair_th = th;
+        const long long tiles64 = tiles_x * ((a.oh + th - 1) / th) * b.nframes;
+        const unsigned g2 = (unsigned) (tiles64 < (long long) sm_count ? tiles64 : (long long) sm_count);
+        const bool small = tiles64 < 4ll * sm_count * kPairWarps;
+        const cudaError_t le = launch_pdl(k_rescale_pair, g2, kPairWarps * 32,
+                                          pair_layout_bytes((unsigned) g_dyn_smem_base, b.enc_blog_cells, 0, kPairWarps, kPairRowInfo), st,
+                                          pdl_enabled(small), b);
+        note_launch();
+        if (le != cudaSuccess) return (int) le;
       } else if (a.iw <= a.ow && !no_cols2 && (elog || smem_u <= kMaxDynSmem)) {
         // horizontal scale <= 1: two adjacent columns per thread share their middle texel
         const long long tiles64 = (long long) ((a.ow + 63) / 64) * ((a.oh + kWalkTH - 1) / kWalkTH) * b.nframes;
