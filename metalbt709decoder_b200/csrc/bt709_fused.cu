@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(const FusedArgs a
   const unsigned spitch = a.spitch;
   for (unsigned u = blockIdx.x; u < units; u += gridDim.x) {
     const unsigned f = u / (unsigned) a.bands, band = u - f * (unsigned) a.bands;
-    const int oy0 = (int) band * kWalkTH;
-    const int oyl = min(oy0 + kWalkTH, p.oh) - 1;
+    const int oy0 = (int) band * a.band_rows;
+    const int oyl = min(oy0 + a.band_rows, p.oh) - 1;
     // source rows of the band: top tap of its first row .. bottom tap of its last row, same float32 steps as the walker
     const float sy0 = __fadd_rn(__fmul_rn(__fadd_rn((float) oy0, 0.5f), p.scale_y), -0.5f);
     const float syl = __fadd_rn(__fmul_rn(__fadd_rn((float) oyl, 0.5f), p.scale_y), -0.5f);
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kFusedWarps * 32, 1) k_fused(const FusedArgs a
     // ---- phase B: pass 2 over the slice; row y of the frame is slice row y - 2 * rp0
     const uint8_t *src = scr - (long long) (2 * rp0) * spitch;
     uint8_t *dst = p.out + (long long) f * p.so;
-    for (int tx = warp; tx < tiles_x; tx += nwarps) pair_tile<false, false, kPairNP, false, kFusedPD>(p, c, src, spitch, dst, tx * TW, oy0, lane, pol_last);
+    for (int tx = warp; tx < tiles_x; tx += nwarps) pair_tile<false, false, kPairNP, false, kFusedPD>(p, c, src, spitch, dst, tx * TW, oy0, lane, pol_last, a.band_rows);
     __syncthreads();  // every warp is done reading before the next band overwrites the slice
   }
 }
@@ -148,11 +148,14 @@ int launch_fused(const DecodeArgs &d0, const RescaleArgs &r0, uint8_t *scratch, 
   const size_t smem = pair_layout_bytes((unsigned) g_dyn_smem_base, r.enc_blog_cells, dec_bytes, kFusedWarps, kWalkRowInfo);
   if (smem > kMaxDynSmem) return -1;
   FusedArgs a{};
-  a.bands = (r.oh + kWalkTH - 1) / kWalkTH;
+  // band height: kWalkTH rows, halved while the call has fewer (frame, band) units than SMs (a CTA works on one unit)
+  a.band_rows = kWalkTH;
+  while (a.band_rows > 16 && (long long) d.nframes * ((r.oh + a.band_rows - 1) / a.band_rows) < (long long) sm_count) a.band_rows >>= 1;
+  a.bands = (r.oh + a.band_rows - 1) / a.band_rows;
   const long long units = (long long) d.nframes * a.bands;
   if (units >= (1ll << 31)) return -1;
   // rows a band can need: its source span, both taps, rounding to chroma row pairs, and the walker's prefetch overrun
-  const int rows_max = (int) ((double) kWalkTH * (double) r.ih / (double) r.oh) + 8 + kFusedPD + 2;
+  const int rows_max = (int) ((double) a.band_rows * (double) r.ih / (double) r.oh) + 8 + kFusedPD + 2;
   a.spitch = (unsigned) (((size_t) d.w * 4 + 255) & ~(size_t) 255);
   a.cta_stride = (long long) rows_max * a.spitch;
   // one CTA per SM, fewer when there are fewer units or the scratch area has room for fewer slices

@@ -129,7 +129,8 @@ struct FusedArgs {
   uint8_t *scratch;   // device memory, gridDim.x * cta_stride bytes
   long long cta_stride;
   unsigned spitch;    // bytes per scratch row (>= w * 4, multiple of 16)
-  int bands;          // ceil(oh / 64)
+  int bands;          // ceil(oh / band_rows)
+  int band_rows;      // output rows per band: kWalkTH, less for calls with fewer bands than SMs
 };
 
 // number of kernels the calling thread has launched through the launchers below (bt709_launch_count accounting)
