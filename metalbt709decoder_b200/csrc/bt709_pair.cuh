@@ -29,14 +29,15 @@ constexpr int kWalkRowInfo = (kWalkTH + 1) * 4;  // words of row info per warp (
 //     gather is a single conflict-free wavefront for any content, for one extra packed add per pair of lookups;
 //   * the alpha byte -> float step is arithmetic (PRMT + packed add + packed multiply), not a table.
 // Same row-info slices, unclamped row walk and three-row register prefetch queue as k_rescale_cols2.
-// k_rescale_pair: 16 warps x 128 registers, taps fetched 3 rows ahead (150.8 k frames/s on 1080p -> 1440p against
-// 143.4 k with 20 warps x 96 registers and 2 rows ahead; 24 warps x 80 registers: 126 k).  The fused kernel keeps 20
-// warps: its decode phase needs them to cover the load latency.
+// k_rescale_pair: 20 warps x 96 registers, taps fetched 2 rows ahead.  Measured on 1080p -> 1440p (k frames/s) after the
+// inner-tile walker, the 9-conversion blend and the CTA-by-CTA tile order: 20 x 96 / 2 rows 158.5, 16 x 128 / 2 rows 155.9,
+// 16 x 128 / 3 rows 155.3, 16 x 128 / 4 rows 152.6; before them 16 x 128 / 3 rows was the best (150.8 against 143.4 for
+// 20 x 96 / 2 rows and 126 for 24 x 80).  The fused kernel also runs 20 warps, 2 rows ahead.
 #ifndef BT709_PAIR_WARPS
-#define BT709_PAIR_WARPS 16
+#define BT709_PAIR_WARPS 20
 #endif
 #ifndef BT709_PAIR_PD
-#define BT709_PAIR_PD 3
+#define BT709_PAIR_PD 2
 #endif
 #ifndef BT709_PAIR_NP
 #define BT709_PAIR_NP 2

@@ -497,3 +497,59 @@ def test_fused_full_batch_checksum_against_two_passes():
     C.decode_rescale_nv12_fused(3, ty, tc, scratch, got, wait=True)
     assert C.launch_count == n0 + 1
     assert torch.equal(got, want)
+
+
+# ------------------------------------------------------------------ calls of a few frames (session 24)
+@pytest.mark.parametrize("F", [1, 4, 9])
+def test_rescale_tile_height_follows_the_batch_size(F):
+    """k_rescale_pair halves its tile height (64 -> 32 -> 16 output rows) while a call has fewer tiles than the grid has
+    warps, and deals the tiles out CTA by CTA: 1, 4 and 9 frames of 1080p -> 1440p run with 16-, 32- and 64-row tiles.
+    Every frame must equal the oracle (two distinct sources, alternating)."""
+    from _gpu import ctx, dev
+    srcs = [bgra_random(1920, 1080, seed=41 + i, alpha=255) for i in range(2)]
+    wants = [ORA.rescale_bgra(s_, 2560, 1440) for s_ in srcs]
+    tin = torch.stack([dev(srcs[f % 2]) for f in range(F)])
+    out = torch.zeros((F, 1440, 2560, 4), dtype=torch.uint8, device="cuda")
+    ctx().rescale_bgra(tin, out, wait=True)
+    for f in range(F):
+        assert torch.equal(out[f].cpu(), torch.from_numpy(wants[f % 2])), f"frame {f} of {F}"
+
+
+def test_back_to_back_small_calls_are_ordered():
+    """Small calls are launched with programmatic stream serialization (the next kernel may start while the previous one
+    drains) and wait in the kernel before they touch global memory.  A chain decode -> rescale -> encode per frame, twelve
+    frames back to back on one stream with NO host synchronisation, the decode output and the rescaled image in buffers
+    that every iteration overwrites (write-after-read against the previous iteration's consumer), must give the oracle's
+    result for every frame."""
+    from _gpu import ctx, dev
+    w, h, ow, oh, n = 256, 64, 384, 96, 12
+    c = ctx()
+    frames = [frame_random(w, h, seed=900 + i) for i in range(n)]
+    ty = [dev(y)[None] for y, _ in frames]
+    tc = [dev(cc)[None] for _, cc in frames]
+    mid = torch.zeros((1, h, w, 4), dtype=torch.uint8, device="cuda")     # shared by all iterations
+    big = torch.zeros((1, oh, ow, 4), dtype=torch.uint8, device="cuda")   # shared by all iterations
+    ey = [torch.zeros((1, oh, ow), dtype=torch.uint8, device="cuda") for _ in range(n)]
+    ec = [torch.zeros((1, oh // 2, ow), dtype=torch.uint8, device="cuda") for _ in range(n)]
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for i in range(n):
+            c.decode_nv12(GAMMA_BT709, ty[i], tc[i], mid, stream=s)
+            c.rescale_bgra(mid, big, stream=s)
+            c.encode_bgra_to_nv12(GAMMA_SRGB, GAMMA_APPLE, big, ey[i], ec[i], stream=s)
+    s.synchronize()
+    for i in range(n):
+        y, cc = frames[i]
+        want_big = ORA.rescale_bgra(ORA.decode_nv12(GAMMA_BT709, y, cc), ow, oh)
+        wy, wc = ORA.encode_bgra_nv12(GAMMA_SRGB, GAMMA_APPLE, want_big)
+        assert np.array_equal(ey[i][0].cpu().numpy(), wy) and np.array_equal(ec[i][0].cpu().numpy(), wc), f"frame {i}"
+    # the same chain through the two-pass policy entry and the fused entry
+    with torch.cuda.stream(s):
+        for i in range(n):
+            c.decode_rescale_nv12(GAMMA_BT709, ty[i], tc[i], mid, big, stream=s)
+            c.encode_bgra_to_nv12(GAMMA_SRGB, GAMMA_APPLE, big, ey[i], ec[i], stream=s)
+    s.synchronize()
+    for i in (0, 5, n - 1):
+        y, cc = frames[i]
+        wy, wc = ORA.encode_bgra_nv12(GAMMA_SRGB, GAMMA_APPLE, ORA.rescale_bgra(ORA.decode_nv12(GAMMA_BT709, y, cc), ow, oh))
+        assert np.array_equal(ey[i][0].cpu().numpy(), wy) and np.array_equal(ec[i][0].cpu().numpy(), wc), f"two-pass frame {i}"
