@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
                     [--workload c2_1080p|c3_uhd|c2_rescale|c2_twopass|c2_fused|c4_alpha|c5_encode]
-                    [--gamma bt709|apple|srgb|linear] [--no-configs] [--no-e2e]
+                    [--gamma bt709|apple|srgb|linear] [--no-configs] [--no-e2e] [--no-live-traffic]
 
 Metric (BASELINE.json): Gpix/s of BT.709 4:2:0 -> sRGB BGRA8, plus % of the HBM roofline.
 A "step" is one pass of the hot path over one resident batch of synthetic frames (configs[1]:
@@ -15,6 +15,9 @@ torch.distributed is used only for the barrier and for reducing the timing scala
 The JSON line also carries `configs`: every other BASELINE configuration (UHD batch, RGB + alpha, pass 2 alone,
 two-pass and fused decode -> rescale, the 4:2:0 encode) timed in the same run, each with its own value,
 roofline fraction and clock record (single-GPU runs only; --no-configs skips them).
+`roofline.traffic` of the headline is read from the DRAM counters in the same run (a child process under
+`ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`, outside the timed regions; --no-live-traffic or a missing
+ncu falls back to the committed constants of profiles/traffic.json, and `traffic_source` says which).
 
 `e2e` is the same metric through the reference-facing host API (MetalBT709Decoder_decodeBT709
 with pinned HOST buffers): upload, kernel and read-back are all inside the timed region; its output is
@@ -152,6 +155,72 @@ def ncu_traffic(kind, pixels_per_launch):
         except Exception:
             return None
     return None
+
+
+_KERNELS_OF = {"decode": "k_decode", "alpha": "k_decode", "rescale": "k_rescale", "fused": "k_fused", "encode": "k_encode",
+               "twopass": "k_decode|k_rescale"}
+
+
+def live_traffic(workload, gamma_name, kind, w, h):
+    """DRAM bytes per pixel of this workload's kernel(s), read from the hardware counters IN THIS RUN: a child process
+    (`bench.py --traffic-probe`, three untimed steps of the same workload on a batch still far larger than L2) runs under
+    `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`, one launch (two for the two-pass step) is captured after
+    two warm-up steps.  Outside every timed region.  Returns (bytes per pixel, note) or (None, why not)."""
+    import shutil
+    import tempfile
+    if any(k.startswith(("NV_NSIGHT", "NVTX_INJECTION", "CUDA_INJECTION")) for k in os.environ):
+        return None, "running under a profiler"
+    ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.exists("/usr/local/cuda/bin/ncu") else None)
+    if not ncu:
+        return None, "ncu not found"
+    frames = max(8, int(300 * (1920 * 1080) / float(w * h)))  # >= 3 GB per launch: the L2 carry-over is ~2 %, as in the bench
+    per_step = 2 if kind == "twopass" else 1
+    log = tempfile.NamedTemporaryFile(suffix=".csv", delete=False).name
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           "regex:" + _KERNELS_OF[kind], "-s", str(2 * per_step), "-c", str(per_step), "--csv", "--log-file", log,
+           sys.executable, os.path.abspath(__file__), "--traffic-probe", "--workload", workload, "--gamma", gamma_name,
+           "--frames", str(frames)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
+        if r.returncode != 0:
+            return None, "ncu probe failed (rc %d)" % r.returncode
+        import csv
+        rows = [x for x in csv.reader(open(log)) if len(x) > 10]
+        ix = {n: i for i, n in enumerate(rows[0])}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        total, seen = 0.0, 0
+        for x in rows[1:]:
+            if x[ix["Metric Name"]] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                total += float(x[ix["Metric Value"]].replace(",", "")) * scale[x[ix["Metric Unit"]]]
+                seen += 1
+        if seen != 2 * per_step:
+            return None, "ncu probe captured %d of %d counters" % (seen, 2 * per_step)
+        return total / (float(frames) * w * h), ("dram__bytes_read.sum + dram__bytes_write.sum read by ncu in this run (child process, "
+                                                 "%d frames, %d launch%s captured after two warm-up steps), scaled to this launch"
+                                                 % (frames, per_step, "" if per_step == 1 else "es"))
+    except Exception as e:  # the constants of profiles/traffic.json stay
+        return None, "ncu probe failed (%s)" % type(e).__name__
+    finally:
+        try:
+            os.unlink(log)
+        except OSError:
+            pass
+
+
+def run_traffic_probe(args):
+    """child of live_traffic: three steps of the workload, nothing printed"""
+    import torch
+    import metalbt709decoder_b200 as pkg
+    w, h, frames, kind = WORKLOADS[args.workload]
+    frames = args.frames or frames
+    gamma = 1 if kind == "alpha" else GAMMAS[args.gamma]
+    ctx = pkg.BT709Context(0)
+    d = make_batch(torch, w, h, frames, 709, kind)
+    step = make_step(ctx, d, kind, gamma, torch.cuda.current_stream())
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    return 0
 
 
 # ------------------------------------------------------------------------- CPU reference
@@ -318,13 +387,22 @@ def make_step(ctx, d, kind, gamma, stream):
     raise ValueError(kind)
 
 
-def roofline_of(kind, w, h, frames, avg_step_s, launches_per_step):
+def roofline_of(kind, w, h, frames, avg_step_s, launches_per_step, live=None):
+    """live: (bytes per pixel, note) from live_traffic, else the committed constants of profiles/traffic.json.
+    `traffic` is per launch like `achieved` (two-pass: the mean of its two launches)."""
     peak, peak_src = measured_peak_gbs()
     ach = algorithmic_bytes(kind, w, h, frames) / avg_step_s / 1e9
+    if live and live[0] is not None:
+        traffic, traffic_src = live[0] * float(frames) * w * h / launches_per_step, live[1]
+    else:
+        traffic = ncu_traffic(kind, float(frames) * w * h / launches_per_step)
+        traffic_src = ("profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per pixel of the "
+                       "committed `ncu --set full` capture of this kernel, scaled to this launch")
+        if live and live[1]:
+            traffic_src += " (live probe: %s)" % live[1]
     return {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-            "traffic": ncu_traffic(kind, float(frames) * w * h / launches_per_step), "peak_source": peak_src,
-            "traffic_source": "profiles/traffic.json: dram__bytes_read.sum + dram__bytes_write.sum per pixel of the "
-                              "committed `ncu --set full` capture of this kernel, scaled to this launch",
+            "traffic": traffic, "peak_source": peak_src,
+            "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": algorithmic_bytes(kind, w, h, frames) / launches_per_step,
             "avg_launch_ms": avg_step_s * 1e3 / launches_per_step, "kernels_per_step": launches_per_step}
 
@@ -475,6 +553,8 @@ def run_b200(args):
     if rank == 0:
         avg_step_s = (sum(per_step_ms) / len(per_step_ms)) / 1e3
         launches_per_step = max(1, launches // max(1, args.steps))
+        # DRAM traffic of the headline kernel from the counters, in this run (single GPU; outside the timed regions)
+        live = live_traffic(args.workload, args.gamma, kind, w, h) if world == 1 and not args.no_live_traffic else None
         cpu = cpu_baseline(gamma, w, h)[0] if world == 1 else None
         line = {
             "metric": "Gpix/s BT.709 4:2:0->sRGB BGRA8", "value": all_units / secs / 1e9, "unit": "Gpix/s",
@@ -483,7 +563,7 @@ def run_b200(args):
             "data": "synthetic",
             "config": config_of(args, frames, world),  # the same object the reference arm prints
             "fps": all_units / (w * h) / secs,
-            "roofline": roofline_of(kind, w, h, frames, avg_step_s, launches_per_step),
+            "roofline": roofline_of(kind, w, h, frames, avg_step_s, launches_per_step, live),
             "cpu_baseline": cpu,
             "e2e": e2e if e2e else {"value": None, "unit": "Gpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                                     "note": "e2e is measured on the decode workloads"},
@@ -609,7 +689,12 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override frames per GPU")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the `configs` array (the other BASELINE configurations)")
+    ap.add_argument("--no-live-traffic", action="store_true",
+                    help="roofline.traffic from the committed constants instead of an ncu child process in this run")
+    ap.add_argument("--traffic-probe", action="store_true", help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.traffic_probe:
+        return run_traffic_probe(args)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
