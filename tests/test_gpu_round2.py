@@ -553,3 +553,51 @@ def test_back_to_back_small_calls_are_ordered():
         y, cc = frames[i]
         wy, wc = ORA.encode_bgra_nv12(GAMMA_SRGB, GAMMA_APPLE, ORA.rescale_bgra(ORA.decode_nv12(GAMMA_BT709, y, cc), ow, oh))
         assert np.array_equal(ey[i][0].cpu().numpy(), wy) and np.array_equal(ec[i][0].cpu().numpy(), wc), f"two-pass frame {i}"
+
+
+def test_small_calls_captured_in_a_cuda_graph():
+    """The same chain (decode -> rescale -> encode per frame, shared intermediates) captured once into a CUDA graph and
+    replayed: launches with programmatic stream serialization become programmatic dependency edges of the graph; the
+    replay must still give the oracle's result for every frame, and again after the inputs have been changed in place."""
+    from _gpu import ctx, dev
+    w, h, ow, oh, n = 256, 64, 384, 96, 6
+    c = ctx()
+    frames = [frame_random(w, h, seed=950 + i) for i in range(n)]
+    ty = [dev(y)[None] for y, _ in frames]
+    tc = [dev(cc)[None] for _, cc in frames]
+    mid = torch.zeros((1, h, w, 4), dtype=torch.uint8, device="cuda")
+    big = torch.zeros((1, oh, ow, 4), dtype=torch.uint8, device="cuda")
+    ey = [torch.zeros((1, oh, ow), dtype=torch.uint8, device="cuda") for _ in range(n)]
+    ec = [torch.zeros((1, oh // 2, ow), dtype=torch.uint8, device="cuda") for _ in range(n)]
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):  # warm-up outside the capture (module loading, attribute calls)
+        c.decode_nv12(GAMMA_BT709, ty[0], tc[0], mid, stream=s)
+        c.rescale_bgra(mid, big, stream=s)
+        c.encode_bgra_to_nv12(GAMMA_SRGB, GAMMA_APPLE, big, ey[0], ec[0], stream=s)
+    s.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=s):
+        cur = torch.cuda.current_stream()
+        for i in range(n):
+            c.decode_nv12(GAMMA_BT709, ty[i], tc[i], mid, stream=cur)
+            c.rescale_bgra(mid, big, stream=cur)
+            c.encode_bgra_to_nv12(GAMMA_SRGB, GAMMA_APPLE, big, ey[i], ec[i], stream=cur)
+
+    def check(fr, tag):
+        for i in range(n):
+            y, cc = fr[i]
+            wy, wc = ORA.encode_bgra_nv12(GAMMA_SRGB, GAMMA_APPLE, ORA.rescale_bgra(ORA.decode_nv12(GAMMA_BT709, y, cc), ow, oh))
+            assert np.array_equal(ey[i][0].cpu().numpy(), wy) and np.array_equal(ec[i][0].cpu().numpy(), wc), f"{tag} frame {i}"
+
+    for t in ey + ec:
+        t.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    check(frames, "first replay")
+    frames2 = [frame_random(w, h, seed=990 + i) for i in range(n)]
+    for i in range(n):
+        ty[i].copy_(dev(frames2[i][0])[None])
+        tc[i].copy_(dev(frames2[i][1])[None])
+    g.replay()
+    torch.cuda.synchronize()
+    check(frames2, "second replay")
