@@ -322,7 +322,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
 //   * running 64-bit pointers (two adds per step each) instead of offset + wrap + LEA pairs.
 // COMPACT: no pad area in the stage (the 209 KB log-cell LUT of the Linear mode leaves room for 30 compact
 // ring slices); the idle lanes are then predicated off instead.
-template <int CL2, int RL2, bool ALPHA, int D, bool COMPACT, bool EARLY>
+// RAGGED: the width is even but not a multiple of 128 (720, 960, 1440 ...): the last tile column is partial.  A warp keeps
+// its tile column, so what changes is per-lane and loop-invariant: the source size of the lane's 16-byte copy (0..16
+// bytes, the rest is zero-filled) and whether the lane stores 16, 8 (w % 4 == 2) or no bytes per row.
+template <int CL2, int RL2, bool ALPHA, int D, bool COMPACT, bool EARLY, bool RAGGED = false>
 __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = CL2 > 0 ? 1 << CL2 : 1, R = 1 << RL2;
@@ -367,7 +370,9 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   const uint8_t *src = role < 2 ? p.y + ((long long) rp0 * 2 + role) * p.py : p.c + (long long) rp0 * p.pc;
   src += tile * 128 + sub * 16;
   const long long sinc = role < 2 ? (long long) drp * 2 * p.py : (long long) drp * p.pc;
-  const uint32_t ssize = role < 3 ? 16u : 0u;
+  // bytes of this lane's 16-byte chunk that lie inside the row (Y and CbCr rows are both w bytes for an even w)
+  const int chunk_left = RAGGED ? min(max(p.w - (int) (tile * 128 + sub * 16), 0), 16) : 16;
+  const uint32_t ssize = role < 3 ? (uint32_t) chunk_left : 0u;
   const uint32_t cdst = ring + role * 128 + sub * 16;
   // alpha stream (ALPHA only): lanes 0-7 row 0, 8-15 row 1, the rest zero fill
   const uint8_t *asrc = nullptr;
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   if (ALPHA) {
     asrc = p.a + ((long long) rp0 * 2 + (role & 1)) * p.pa + tile * 128 + sub * 16;
     ainc = (long long) drp * 2 * p.pa;
-    asize = role < 2 ? 16u : 0u;
+    asize = role < 2 ? (uint32_t) chunk_left : 0u;
   }
   auto issue = [&](int slot) {
     if (COMPACT) {
@@ -400,6 +405,7 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
 
   uint8_t *out0 = p.out + (long long) rp0 * 2 * p.po + (size_t) (tile * 32 + lane) * 16;
   const long long po = p.po, oinc = (long long) drp * 2 * p.po;
+  const int px_left = RAGGED ? p.w - (int) (tile * 32 + lane) * 4 : 4;  // pixels of this lane inside the row (even)
 #pragma unroll
   for (int j = 0; j < D - 1; j++) {
     if ((unsigned) j < nsteps) issue(j);
@@ -442,8 +448,15 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
       f32x2 crn = mul2(add2(pku(magic_byte<1>(t.c), magic_byte<3>(t.c)), k.kC), k.inv255);
       f32x2 cb_g = mul2(cbn, k.g_cb), cb_b = mul2(cbn, k.b_cb);
       f32x2 cr_r = mul2(crn, k.r_cr), cr_g = mul2(crn, k.g_cr);
-      st_stream_u128(out0, decode_row<CL2, RL2, ALPHA>(t.y0, t.a0, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
-      st_stream_u128(out0 + po, decode_row<CL2, RL2, ALPHA>(t.y1, t.a1, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase));
+      const uint4 v0 = decode_row<CL2, RL2, ALPHA>(t.y0, t.a0, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase);
+      const uint4 v1 = decode_row<CL2, RL2, ALPHA>(t.y1, t.a1, cb_g, cb_b, cr_r, cr_g, k, clamp_lo, sbase);
+      if (!RAGGED || px_left >= 4) {
+        st_stream_u128(out0, v0);
+        st_stream_u128(out0 + po, v1);
+      } else if (px_left == 2) {
+        st_stream_u64(out0, make_uint2(v0.x, v0.y));
+        st_stream_u64(out0 + po, make_uint2(v1.x, v1.y));
+      }
       out0 += oinc;
     }
   }
@@ -869,8 +882,12 @@ __global__ void __launch_bounds__(1024, 1) k_decode_reg(const DecodeArgs p) {
 // the power cap has pulled the clocks down.  The Linear mode and the alpha variant are faster with 3l either way
 // (Linear 1012 vs 966 in a burst).  BT709_RING=2e|3l overrides the choice.
 // k_decode_lin for a contiguous batch of full tiles (decoded as one tall image).  Returns -1 when it does not apply.
-template <int CL2, int RL2, bool ALPHA, bool COMPACT, int D, bool EARLY>
+template <int CL2, int RL2, bool ALPHA, bool COMPACT, int D, bool EARLY, bool RAGGED = false>
 static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
+  if constexpr (!RAGGED && !COMPACT) {  // partial last tile column: the same kernel with per-lane copy sizes and store widths
+    if (a0.w % 128 != 0) return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, D, EARLY, true>(a0, sm_count, s);
+  }
+  if (!RAGGED && a0.w % 128 != 0) return -1;  // (the compact stage has no zero-fill form)
   DecodeArgs a = a0;
   a.h *= a.nframes;
   a.rows2 *= a.nframes;
@@ -894,7 +911,12 @@ static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s
   // back-to-back calls on one stream (the reference's one-frame-per-call pattern) overlap this launch's scheduling
   // with the previous kernel's tail; the kernel waits (griddepcontrol.wait) before it touches global memory.
   // BT709_PDL=0 disables it, BT709_PDL=all applies it to every launch that supports it (pdl_enabled).
-  const cudaError_t le = launch_pdl(k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY>, (unsigned) grid, (unsigned) wpc * 32,
+  if constexpr (RAGGED) {  // opt-in to the dynamic shared memory here: the full-width instantiations are set up at init
+    static const int attr_rc = (int) cudaFuncSetAttribute(k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY, true>,
+                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+    if (attr_rc) return attr_rc;
+  }
+  const cudaError_t le = launch_pdl(k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY, RAGGED>, (unsigned) grid, (unsigned) wpc * 32,
                                     lut_bytes + (size_t) wpc * slice, s, pdl_enabled(RL2 < 5), a);
   note_launch();
   if (le != cudaSuccess) return (int) le;
@@ -907,7 +929,7 @@ static int launch_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s, 
   static const char *env = getenv("BT709_RING");
   static const char *reg_env = getenv("BT709_REG");  // experiment: register loads, 1-3 tiles ahead (opaque, replicated LUT)
   if constexpr (!ALPHA && !COMPACT && RL2 == 5) {
-    if (reg_env) {
+    if (reg_env && a.w % 128 == 0) {
       DecodeArgs b = a;
       b.h *= b.nframes; b.rows2 *= b.nframes; b.nframes = 1;
       const size_t lut_bytes = (((size_t) (CL2 > 0 ? (1 << (CL2 > 0 ? CL2 : 0)) + 1 : b.log_cells) * 32 * 4) + 127) & ~(size_t) 127;
@@ -938,7 +960,8 @@ static int try_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s) {
   static const char *small_env = getenv("BT709_SMALL_STEPS");
   static const int small_steps = small_env ? atoi(small_env) : 4;
   if (off) return -1;
-  if (!((a.w % 128 == 0) && (a.h % 2 == 0))) return -1;
+  static const bool no_ragged = getenv("BT709_NO_RAGGED_LIN") != nullptr;  // reproduction: ragged widths on k_decode_fast
+  if (!((a.w % 2 == 0) && (a.h % 2 == 0)) || (a.w % 128 != 0 && no_ragged)) return -1;
   const bool contiguous = a.nframes == 1 || (a.sy == (long long) a.h * a.py && a.sc == (long long) a.rows2 * a.pc &&
                                              a.so == (long long) a.h * a.po && (!ALPHA || a.sa == (long long) a.h * a.pa));
   if (!contiguous || (long long) a.nframes * a.h >= (1ll << 30)) return -1;

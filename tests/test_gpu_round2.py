@@ -216,6 +216,13 @@ LIN_CASES = [
     (8192, 8, 2, 2, False),      # 64 tiles per row, Linear mode
     (3840, 6, 5, 1, True),       # UHD width with alpha, small call
     (640, 360, 9, 3, False),     # 5 tiles per row
+    # ragged widths: a partial last tile column (per-lane copy sizes, 16- / 8- / 0-byte stores)
+    (720, 480, 3, 3, False),     # 5 full tiles + 80 pixels
+    (960, 540, 2, 2, False),     # 7 full tiles + 64 pixels, Linear mode
+    (1440, 1080, 1, 0, False),   # 11 full tiles + 32 pixels, one frame per call (few-replica LUT)
+    (352, 288, 4, 1, True),      # 2 full tiles + 96 pixels, alpha stream
+    (48, 4, 3, 3, False),        # less than one tile
+    (4240, 4, 2, 1, False),      # 33 full tiles + 16 pixels
 ]
 
 
@@ -601,3 +608,33 @@ def test_small_calls_captured_in_a_cuda_graph():
     g.replay()
     torch.cuda.synchronize()
     check(frames2, "second replay")
+
+
+@pytest.mark.parametrize("w,pitch,h,F,gamma,alpha", [(854, 896, 480, 2, 3, False), (1366, 1376, 768, 1, 0, False),
+                                                    (854, 864, 6, 3, 1, True), (1366, 1376, 10, 2, 2, False)])
+def test_ragged_widths_with_padded_pitches(w, pitch, h, F, gamma, alpha):
+    """Even widths that are not a multiple of 16 in 16-byte-aligned pitched planes (what a hardware decoder hands over):
+    the last 16-byte chunk of a row is copied with a source size of 6 or 14 bytes and the last lane stores 8 bytes
+    (w % 4 == 2).  The padding of the output rows must stay untouched."""
+    from _gpu import ctx, dev
+    frames = [frame_random(w, h, seed=1200 + f, full_range=(f % 2 == 1)) for f in range(F)]
+    ybuf = torch.zeros((F, h, pitch), dtype=torch.uint8, device="cuda")
+    cbuf = torch.zeros((F, h // 2, pitch), dtype=torch.uint8, device="cuda")
+    for f, (y, c) in enumerate(frames):
+        ybuf[f, :, :w] = dev(y)
+        cbuf[f, :, :w] = dev(c)
+    alphas, abuf = None, None
+    if alpha:
+        alphas = [frame_random(w, h, seed=1300 + f, full_range=True)[0] for f in range(F)]
+        abuf = torch.zeros((F, h, pitch), dtype=torch.uint8, device="cuda")
+        for f, a in enumerate(alphas):
+            abuf[f, :, :w] = dev(a)
+    obuf = torch.full((F, h, pitch, 4), 0x5A, dtype=torch.uint8, device="cuda")
+    n0 = ctx().launch_count
+    ctx().decode_nv12(gamma, ybuf[:, :, :w], cbuf[:, :, :w], obuf[:, :, :w], alpha_y=abuf[:, :, :w] if alpha else None, wait=True)
+    assert ctx().launch_count == n0 + 1
+    got = obuf.cpu().numpy()
+    assert (got[:, :, w:] == 0x5A).all(), "row padding overwritten"
+    for f in range(F):
+        want = ORA.decode_nv12(gamma, frames[f][0], frames[f][1], alpha_y=alphas[f] if alpha else None)
+        assert np.array_equal(got[f, :, :w], want), f"{w}x{h} frame {f}: {(got[f, :, :w] != want).sum()} byte mismatches"
