@@ -325,7 +325,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_decode_ring(const DecodeArgs p) 
 // RAGGED: the width is even but not a multiple of 128 (720, 960, 1440 ...): the last tile column is partial.  A warp keeps
 // its tile column, so what changes is per-lane and loop-invariant: the source size of the lane's 16-byte copy (0..16
 // bytes, the rest is zero-filled) and whether the lane stores 16, 8 (w % 4 == 2) or no bytes per row.
-template <int CL2, int RL2, bool ALPHA, int D, bool COMPACT, bool EARLY, bool RAGGED = false>
+// STRIDED: the frames of the batch are not back to back (e.g. one allocation per frame with the CbCr plane right behind
+// the Y plane, what a hardware decoder hands over): the tile sequence still runs over (frame, row pair, tile column) in
+// row-major order, a step is `lin_drp` row pairs = dq whole frames + dr row pairs further, and a pointer gets one extra
+// per-lane constant whenever its row-pair-in-frame counter wraps (one compare and three predicated adds per step on
+// the load side and on the store side).
+template <int CL2, int RL2, bool ALPHA, int D, bool COMPACT, bool EARLY, bool RAGGED = false, bool STRIDED = false>
 __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   extern __shared__ __align__(128) uint32_t s_lut[];
   constexpr int N = CL2 > 0 ? 1 << CL2 : 1, R = 1 << RL2;
@@ -362,14 +367,22 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   const unsigned g = blockIdx.x * (unsigned) p.lin_wpc + warp;
   const unsigned T = (unsigned) p.tiles_per_row, rows2 = (unsigned) p.rows2, drp = (unsigned) p.lin_drp;
   const unsigned rp0 = g / T, tile = g - rp0 * T;
+  const unsigned total_rp = STRIDED ? (unsigned) p.nframes * rows2 : rows2;  // (contiguous: the launcher folded the frames into rows2)
   // (a warp without work still fills its share of the LUT and meets the CTA barrier below)
-  const unsigned nsteps = g < (unsigned) p.lin_warps && rp0 < rows2 ? (rows2 - rp0 + drp - 1) / drp : 0u;
+  const unsigned nsteps = g < (unsigned) p.lin_warps && rp0 < total_rp ? (total_rp - rp0 + drp - 1) / drp : 0u;
+  // STRIDED: (frame, row pair in the frame) of the first tile; a step = dq frames + dr row pairs
+  const unsigned f0 = STRIDED ? rp0 / rows2 : 0u, r0 = STRIDED ? rp0 - f0 * rows2 : rp0;
+  const unsigned dq = STRIDED ? drp / rows2 : 0u, dr = STRIDED ? drp - dq * rows2 : drp;
 
   // ---- copy role of this lane: lanes 0-7 Y row 0, 8-15 Y row 1, 16-23 the CbCr row, 24-31 zero fill
   const int role = lane >> 3, sub = lane & 7;
-  const uint8_t *src = role < 2 ? p.y + ((long long) rp0 * 2 + role) * p.py : p.c + (long long) rp0 * p.pc;
+  const uint8_t *src = role < 2 ? p.y + (long long) f0 * p.sy + ((long long) r0 * 2 + role) * p.py
+                                : p.c + (long long) f0 * p.sc + (long long) r0 * p.pc;
   src += tile * 128 + sub * 16;
-  const long long sinc = role < 2 ? (long long) drp * 2 * p.py : (long long) drp * p.pc;
+  const long long sinc = role < 2 ? (long long) dq * p.sy + (long long) dr * 2 * p.py : (long long) dq * p.sc + (long long) dr * p.pc;
+  // extra step when the row pair wraps into the next frame
+  const long long swrap = role < 2 ? p.sy - (long long) rows2 * 2 * p.py : p.sc - (long long) rows2 * p.pc;
+  unsigned rl = r0;  // row pair in the frame of the next stage to be issued
   // bytes of this lane's 16-byte chunk that lie inside the row (Y and CbCr rows are both w bytes for an even w)
   const int chunk_left = RAGGED ? min(max(p.w - (int) (tile * 128 + sub * 16), 0), 16) : 16;
   const uint32_t ssize = role < 3 ? (uint32_t) chunk_left : 0u;
@@ -378,9 +391,11 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
   const uint8_t *asrc = nullptr;
   long long ainc = 0;
   uint32_t asize = 0;
+  long long awrap = 0;
   if (ALPHA) {
-    asrc = p.a + ((long long) rp0 * 2 + (role & 1)) * p.pa + tile * 128 + sub * 16;
-    ainc = (long long) drp * 2 * p.pa;
+    asrc = p.a + (long long) f0 * p.sa + ((long long) r0 * 2 + (role & 1)) * p.pa + tile * 128 + sub * 16;
+    ainc = (long long) dq * p.sa + (long long) dr * 2 * p.pa;
+    awrap = p.sa - (long long) rows2 * 2 * p.pa;
     asize = role < 2 ? (uint32_t) chunk_left : 0u;
   }
   auto issue = [&](int slot) {
@@ -401,10 +416,20 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
       }
       asrc += ainc;
     }
+    if (STRIDED) {
+      rl += dr;
+      if (rl >= rows2) {
+        rl -= rows2;
+        src += swrap;
+        if (ALPHA) asrc += awrap;
+      }
+    }
   };
 
-  uint8_t *out0 = p.out + (long long) rp0 * 2 * p.po + (size_t) (tile * 32 + lane) * 16;
-  const long long po = p.po, oinc = (long long) drp * 2 * p.po;
+  uint8_t *out0 = p.out + (long long) f0 * p.so + (long long) r0 * 2 * p.po + (size_t) (tile * 32 + lane) * 16;
+  const long long po = p.po, oinc = (long long) dq * p.so + (long long) dr * 2 * p.po;
+  const long long owrap = p.so - (long long) rows2 * 2 * p.po;
+  unsigned ro = r0;  // row pair in the frame of the tile being stored
   const int px_left = RAGGED ? p.w - (int) (tile * 32 + lane) * 4 : 4;  // pixels of this lane inside the row (even)
 #pragma unroll
   for (int j = 0; j < D - 1; j++) {
@@ -458,6 +483,13 @@ __global__ void __launch_bounds__(1024, 1) k_decode_lin(const DecodeArgs p) {
         st_stream_u64(out0 + po, make_uint2(v1.x, v1.y));
       }
       out0 += oinc;
+      if (STRIDED) {
+        ro += dr;
+        if (ro >= rows2) {
+          ro -= rows2;
+          out0 += owrap;
+        }
+      }
     }
   }
 }
@@ -882,16 +914,22 @@ __global__ void __launch_bounds__(1024, 1) k_decode_reg(const DecodeArgs p) {
 // the power cap has pulled the clocks down.  The Linear mode and the alpha variant are faster with 3l either way
 // (Linear 1012 vs 966 in a burst).  BT709_RING=2e|3l overrides the choice.
 // k_decode_lin for a contiguous batch of full tiles (decoded as one tall image).  Returns -1 when it does not apply.
-template <int CL2, int RL2, bool ALPHA, bool COMPACT, int D, bool EARLY, bool RAGGED = false>
-static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s) {
+template <int CL2, int RL2, bool ALPHA, bool COMPACT, int D, bool EARLY, bool RAGGED = false, bool STRIDED = false>
+static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s, bool strided = false) {
   if constexpr (!RAGGED && !COMPACT) {  // partial last tile column: the same kernel with per-lane copy sizes and store widths
-    if (a0.w % 128 != 0) return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, D, EARLY, true>(a0, sm_count, s);
+    if (a0.w % 128 != 0) return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, D, EARLY, true, STRIDED>(a0, sm_count, s, strided);
   }
   if (!RAGGED && a0.w % 128 != 0) return -1;  // (the compact stage has no zero-fill form)
+  if constexpr (!STRIDED && !COMPACT && RL2 == 5) {  // frames that are not back to back: the wrap-aware instantiation (batches only)
+    if (strided) return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, D, EARLY, RAGGED, true>(a0, sm_count, s, true);
+  }
+  if (!STRIDED && strided) return -1;
   DecodeArgs a = a0;
-  a.h *= a.nframes;
-  a.rows2 *= a.nframes;
-  a.nframes = 1;
+  if (!STRIDED) {
+    a.h *= a.nframes;
+    a.rows2 *= a.nframes;
+    a.nframes = 1;
+  }
   const size_t lut_bytes = (((size_t) (CL2 > 0 ? (1 << CL2) + 1 : a.log_cells) * (1 << RL2) * 4) + 127) & ~(size_t) 127;
   if (lut_bytes >= kMaxDynSmem) return -1;
   const size_t slice = (size_t) D * (COMPACT ? (ALPHA ? 640 : 384) : (ALPHA ? 1024 : 512));
@@ -899,7 +937,7 @@ static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s
   if (wpc > 32) wpc = 32;
   if (wpc < 8) return -1;
   const unsigned T = (unsigned) a.tiles_per_row;
-  const unsigned long long total_tiles = (unsigned long long) a.rows2 * T;
+  const unsigned long long total_tiles = (unsigned long long) a.nframes * a.rows2 * T;
   unsigned long long grid = (total_tiles + wpc - 1) / wpc;
   if (grid > (unsigned long long) sm_count) grid = sm_count;
   const unsigned W = (unsigned) grid * wpc;
@@ -911,12 +949,12 @@ static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s
   // back-to-back calls on one stream (the reference's one-frame-per-call pattern) overlap this launch's scheduling
   // with the previous kernel's tail; the kernel waits (griddepcontrol.wait) before it touches global memory.
   // BT709_PDL=0 disables it, BT709_PDL=all applies it to every launch that supports it (pdl_enabled).
-  if constexpr (RAGGED) {  // opt-in to the dynamic shared memory here: the full-width instantiations are set up at init
-    static const int attr_rc = (int) cudaFuncSetAttribute(k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY, true>,
+  if constexpr (RAGGED || STRIDED) {  // opt-in to the dynamic shared memory here: the plain instantiations are set up at init
+    static const int attr_rc = (int) cudaFuncSetAttribute(k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY, RAGGED, STRIDED>,
                                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
     if (attr_rc) return attr_rc;
   }
-  const cudaError_t le = launch_pdl(k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY, RAGGED>, (unsigned) grid, (unsigned) wpc * 32,
+  const cudaError_t le = launch_pdl(k_decode_lin<CL2, RL2, ALPHA, D, COMPACT, EARLY, RAGGED, STRIDED>, (unsigned) grid, (unsigned) wpc * 32,
                                     lut_bytes + (size_t) wpc * slice, s, pdl_enabled(RL2 < 5), a);
   note_launch();
   if (le != cudaSuccess) return (int) le;
@@ -925,11 +963,11 @@ static int launch_decode_lin1(const DecodeArgs &a0, int sm_count, cudaStream_t s
 
 // ring choice: BT709_RING=2e|3l, else `late3_default` (see the table above)
 template <int CL2, int RL2, bool ALPHA, bool COMPACT>
-static int launch_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s, bool late3_default) {
+static int launch_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s, bool late3_default, bool strided = false) {
   static const char *env = getenv("BT709_RING");
   static const char *reg_env = getenv("BT709_REG");  // experiment: register loads, 1-3 tiles ahead (opaque, replicated LUT)
   if constexpr (!ALPHA && !COMPACT && RL2 == 5) {
-    if (reg_env && a.w % 128 == 0) {
+    if (reg_env && a.w % 128 == 0 && !strided) {
       DecodeArgs b = a;
       b.h *= b.nframes; b.rows2 *= b.nframes; b.nframes = 1;
       const size_t lut_bytes = (((size_t) (CL2 > 0 ? (1 << (CL2 > 0 ? CL2 : 0)) + 1 : b.log_cells) * 32 * 4) + 127) & ~(size_t) 127;
@@ -948,8 +986,8 @@ static int launch_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s, 
     }
   }
   const bool late3 = env ? (env[0] == '3') : late3_default;
-  if (late3) return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, 3, false>(a, sm_count, s);
-  return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, 2, true>(a, sm_count, s);
+  if (late3) return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, 3, false>(a, sm_count, s, strided);
+  return launch_decode_lin1<CL2, RL2, ALPHA, COMPACT, 2, true>(a, sm_count, s, strided);
 }
 
 // Picks the k_decode_lin instantiation: per-lane replicated LUT for batches, a few replicas (a much shorter
@@ -964,7 +1002,19 @@ static int try_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s) {
   if (!((a.w % 2 == 0) && (a.h % 2 == 0)) || (a.w % 128 != 0 && no_ragged)) return -1;
   const bool contiguous = a.nframes == 1 || (a.sy == (long long) a.h * a.py && a.sc == (long long) a.rows2 * a.pc &&
                                              a.so == (long long) a.h * a.po && (!ALPHA || a.sa == (long long) a.h * a.pa));
-  if (!contiguous || (long long) a.nframes * a.h >= (1ll << 30)) return -1;
+  // Strided batches: measured on the Y|CbCr-per-frame layout (session 36), the wrap-aware instantiation is level with the
+  // round-1 ring kernel on full-width rows (945 vs 940 Gpix/s for 1080p, 944 vs 982 for 2048-wide sRGB: the layout, not
+  // the kernel, costs the 8 % against a contiguous batch) and 23 % faster on ragged widths, which the ring kernel cannot
+  // take (828 vs 674).  So: ragged widths only.  BT709_STRIDED_LIN=all / 0: always / never.
+  static const char *strided_env = getenv("BT709_STRIDED_LIN");
+  const bool strided = !contiguous;
+  const bool no_strided = strided_env ? strided_env[0] == '0' || (strided_env[0] != 'a' && a.w % 128 == 0) : a.w % 128 == 0;
+  // (strided: non-negative strides that keep the frames of a plane apart, so that the wrap constants are what they say)
+  if (strided && (no_strided || a.sy < (long long) a.h * a.py || a.sc < (long long) a.rows2 * a.pc || a.so < (long long) a.h * a.po ||
+                  (ALPHA && a.sa < (long long) a.h * a.pa) || !aligned(a.sy, 16) || !aligned(a.sc, 16) || !aligned(a.so, 16) ||
+                  (ALPHA && !aligned(a.sa, 16))))
+    return -1;
+  if ((long long) a.nframes * a.h >= (1ll << 30)) return -1;
   if (!(aligned(a.y, 16) && aligned(a.py, 16) && aligned(a.c, 16) && aligned(a.pc, 16) && aligned(a.out, 16) && aligned(a.po, 16) &&
         (!ALPHA || (aligned(a.a, 16) && aligned(a.pa, 16)))))
     return -1;
@@ -980,19 +1030,19 @@ static int try_decode_lin(const DecodeArgs &a, int sm_count, cudaStream_t s) {
     b.log_cells = a.blog_cells;
     b.log_first = a.blog_first;
     b.log_bias = a.blog_bias;
-    if (small) return launch_decode_lin<-1, 2, ALPHA, false>(b, sm_count, s, true);
-    return launch_decode_lin<-1, 5, ALPHA, false>(b, sm_count, s, true);
+    if (small) return launch_decode_lin<-1, 2, ALPHA, false>(b, sm_count, s, true, strided);
+    return launch_decode_lin<-1, 5, ALPHA, false>(b, sm_count, s, true, strided);
   }
   if (a.log_lut && a.log_cells > 0) {
     DecodeArgs b = a;
     b.lut = a.log_lut;
     b.clamp_lo = a.log_clamp_lo;
-    if (small) return launch_decode_lin<0, 2, ALPHA, false>(b, sm_count, s, true);
-    return launch_decode_lin<0, 5, ALPHA, true>(b, sm_count, s, true);
+    if (small) return launch_decode_lin<0, 2, ALPHA, false>(b, sm_count, s, true, strided);
+    return launch_decode_lin<0, 5, ALPHA, true>(b, sm_count, s, true, strided);
   }
   if (a.cells_log2 == 10) {
-    if (small) return launch_decode_lin<10, 3, ALPHA, false>(a, sm_count, s, ALPHA);
-    return launch_decode_lin<10, 5, ALPHA, false>(a, sm_count, s, ALPHA);
+    if (small) return launch_decode_lin<10, 3, ALPHA, false>(a, sm_count, s, ALPHA, strided);
+    return launch_decode_lin<10, 5, ALPHA, false>(a, sm_count, s, ALPHA, strided);
   }
   return -1;
 }

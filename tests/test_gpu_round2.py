@@ -638,3 +638,60 @@ def test_ragged_widths_with_padded_pitches(w, pitch, h, F, gamma, alpha):
     for f in range(F):
         want = ORA.decode_nv12(gamma, frames[f][0], frames[f][1], alpha_y=alphas[f] if alpha else None)
         assert np.array_equal(got[f, :, :w], want), f"{w}x{h} frame {f}: {(got[f, :, :w] != want).sum()} byte mismatches"
+
+
+@pytest.mark.parametrize("w,h,F,gamma,alpha,gap", [(1920, 1080, 3, 3, False, 0), (1360, 720, 7, 2, False, 2), (720, 480, 12, 0, False, 1),
+                                                  (2000, 1536, 2, 1, True, 0), (600, 64, 90, 3, False, 3), (96, 2, 9000, 1, False, 1)])
+def test_strided_batches_on_the_linear_tile_stream_kernel(w, h, F, gamma, alpha, gap):
+    """One allocation per frame with the CbCr plane right behind the Y plane (what a hardware decoder hands over), `gap`
+    spare rows between frames, and an output whose frames are not back to back either: the batch is not one tall image.
+    Ragged widths take k_decode_lin's STRIDED instantiation, which steps (frame, row pair) with a wrap (full-width rows
+    stay on the round-1 ring kernel, first case; BT709_STRIDED_LIN=all moves them too, see the subprocess test).  Large
+    enough for the batch kernel (more than 4 steps per warp); the last case moves whole frames per step (dq > 0)."""
+    from _gpu import ctx, dev
+    frames = [frame_random(w, h, seed=1500 + f, full_range=(f % 2 == 1)) for f in range(min(F, 8))]
+    rows = h + h // 2 + gap
+    buf = torch.zeros((F, rows, w), dtype=torch.uint8, device="cuda")
+    for f in range(F):
+        y, c = frames[f % len(frames)]
+        buf[f, :h] = dev(y)
+        buf[f, h:h + h // 2] = dev(c)
+    alphas, abuf = None, None
+    if alpha:
+        alphas = [frame_random(w, h, seed=1600 + f, full_range=True)[0] for f in range(len(frames))]
+        abuf = torch.zeros((F, h + 2, w), dtype=torch.uint8, device="cuda")
+        for f in range(F):
+            abuf[f, :h] = dev(alphas[f % len(frames)])
+    obuf = torch.full((F, h + 1 + gap, w, 4), 0x5A, dtype=torch.uint8, device="cuda")
+    n0 = ctx().launch_count
+    ctx().decode_nv12(gamma, buf[:, :h], buf[:, h:h + h // 2], obuf[:, :h], alpha_y=abuf[:, :h] if alpha else None, wait=True)
+    assert ctx().launch_count == n0 + 1
+    assert bool((obuf[:, h:] == 0x5A).all()), "rows between the output frames overwritten"
+    wants = [torch.from_numpy(ORA.decode_nv12(gamma, *frames[i], alpha_y=alphas[i] if alpha else None)).cuda() for i in range(len(frames))]
+    for f in range(F):
+        assert torch.equal(obuf[f, :h], wants[f % len(frames)]), f"{w}x{h} frame {f} of {F}"
+
+
+def test_strided_full_width_batches_on_both_kernels_in_a_subprocess():
+    """BT709_STRIDED_LIN=all: full-width strided batches on k_decode_lin's STRIDED instantiation instead of the ring kernel"""
+    code = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, "tests")
+from _oracle import Oracle, frame_random
+from _gpu import ctx, dev
+ora = Oracle()
+for (w, h, F, g) in [(1920, 1080, 3, 3), (1280, 720, 7, 2), (128, 2, 9000, 1)]:
+    fr = [frame_random(w, h, seed=1700 + f) for f in range(min(F, 4))]
+    buf = torch.zeros((F, h + h // 2 + 1, w), dtype=torch.uint8, device="cuda")
+    for f in range(F):
+        buf[f, :h] = dev(fr[f % len(fr)][0]); buf[f, h:h + h // 2] = dev(fr[f % len(fr)][1])
+    out = torch.zeros((F, h + 2, w, 4), dtype=torch.uint8, device="cuda")
+    ctx().decode_nv12(g, buf[:, :h], buf[:, h:h + h // 2], out[:, :h], wait=True)
+    wants = [torch.from_numpy(ora.decode_nv12(g, *x)).cuda() for x in fr]
+    for f in range(F):
+        assert torch.equal(out[f, :h], wants[f % len(fr)]), (w, h, g, f)
+print("variant ok")
+'''
+    r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, BT709_STRIDED_LIN="all"), capture_output=True,
+                       text=True, timeout=600)
+    assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout + r.stderr
