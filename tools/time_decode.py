@@ -16,7 +16,9 @@ ctx = pkg.BT709Context(0)
 cw = (w + 1) // 2 * 2
 y = torch.randint(16, 236, (frames, h, w + pad), dtype=torch.uint8, device="cuda")[:, :, :w]
 c = torch.randint(16, 241, (frames, (h + 1) // 2, cw + pad), dtype=torch.uint8, device="cuda")[:, :, :cw]
-out = torch.zeros((frames, h, w + pad, 4), dtype=torch.uint8, device="cuda")[:, :, :w]
+# (encode reads `out`: random BGRA, A = 255 - all-zero input runs 3-5 % faster than real content, the table reads collapse)
+out = (torch.randint(0, 256, (frames, h, w + pad, 4), dtype=torch.uint8, device="cuda") if encode
+       else torch.zeros((frames, h, w + pad, 4), dtype=torch.uint8, device="cuda"))[:, :, :w]
 def run():
     if encode:
         ctx.encode_bgra_to_nv12(gin, gout, out, y, c)
