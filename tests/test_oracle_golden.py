@@ -136,3 +136,29 @@ def test_roundtrip_histograms(impl, key):
     assert got[0] == h["exact"]
     assert got[:len(h["buckets"])] == h["buckets"]
     assert sum(got) == 1 << 24 and sum(got[len(h["buckets"]):]) == 0
+
+
+def test_alpha_plane_against_the_metal_shader_arithmetic():
+    """D12 has no test and no exact CPU twin in the reference ("parity unpinned").  What can be pinned on the CPU: the
+    shader's own float32 arithmetic (AAPLShaders.metal:249-271: (A/255 - 16/255) * 1.1644, saturate, unorm8 store) gives
+    the same byte as the oracle (the CPU near-twin BT709.h:466-513, which multiplies by 255/219) for ALL 256 codes, with
+    round-half-even or half-away alike: the literal 1.1644 never matters (the pre-rounding value stays 0.0044 away from
+    a .5).  If the R8Unorm sample is really delivered as a `half` (the shader declares texture2d<half>), six codes come
+    out one LSB off - the bound of what real Metal hardware can differ from this implementation by."""
+    import numpy as np
+    f32 = np.float32
+    ora = Oracle()
+    ours = np.array([ora.alpha_pixel(a) for a in range(256)])
+
+    def shader(sample):
+        yn = (sample - f32(16.0) / f32(255.0)).astype(np.float32)
+        yn = np.clip((yn * f32(1.1644)).astype(np.float32), 0, 1).astype(np.float32)
+        return (yn * f32(255.0)).astype(np.float32)
+
+    s32 = (np.arange(256).astype(np.float32) / f32(255.0)).astype(np.float32)
+    x = shader(s32)
+    assert np.array_equal(np.rint(x).astype(int), ours) and np.array_equal(np.floor(x + 0.5).astype(int), ours)
+    assert np.abs((x - np.floor(x)) - 0.5).min() > 0.004
+    xh = shader(s32.astype(np.float16).astype(np.float32))
+    d = np.rint(xh).astype(int) - ours
+    assert np.abs(d).max() == 1 and np.nonzero(d)[0].tolist() == [86, 92, 104, 141, 177, 232]
