@@ -165,12 +165,20 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   k.quarter = bc(0.25f); k.rnd = bc(32768.5f); k.nmagic = bc(-8388608.0f);
   k.inv255 = bc(1.0f / 255.0f);
 
-  const unsigned r_local = warp / p.tiles_per_row;
-  if (r_local >= (unsigned) p.rps) return;
-  const unsigned tile0 = warp - r_local * p.tiles_per_row;
+  unsigned tile0, rpg0;
+  if (p.lin_warps) {  // linear tile order: every warp of the CTA has a tile column
+    const unsigned g = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (g >= (unsigned) p.lin_warps) return;
+    rpg0 = g / p.tiles_per_row;
+    tile0 = g - rpg0 * p.tiles_per_row;
+  } else {
+    const unsigned r_local = warp / p.tiles_per_row;
+    if (r_local >= (unsigned) p.rps) return;
+    tile0 = warp - r_local * p.tiles_per_row;
+    rpg0 = blockIdx.x * p.rps + r_local;
+  }
   const unsigned rows2 = p.h / 2;
   const unsigned total_rp = (unsigned) p.nframes * rows2;
-  const unsigned rpg0 = blockIdx.x * p.rps + r_local;
   if (rpg0 >= total_rp) return;
   const unsigned f0 = rpg0 / rows2, rp0 = rpg0 - f0 * rows2;
   const unsigned nsteps = (total_rp - rpg0 + p.step_rp - 1) / p.step_rp;
@@ -332,6 +340,23 @@ static int launch_encode_fast1(const EncodeArgs &a0, int sm_count, cudaStream_t 
   unsigned grid = (total_rp + a.rps - 1) / a.rps;
   if (grid > (unsigned) sm_count) grid = sm_count;
   a.step_rp = grid * a.rps;
+  // rows of 15 or 30 tiles (1920, 3840 wide) leave 2 of the 32 warps idle in the band layout; in a contiguous batch the
+  // tiles can be taken in linear order instead, like the decode (session 40: 1920-wide 862 -> 912 Gpix/s expected from
+  // the 32-warp geometries).  BT709_NO_ENC_LINEAR=1: band layout always.
+  static const bool no_enc_linear = getenv("BT709_NO_ENC_LINEAR") != nullptr;
+  a.lin_warps = 0;
+  if (!wrap && !no_enc_linear && a.tiles_per_row < wpc && wpc % a.tiles_per_row != 0) {
+    const unsigned long long tiles = (unsigned long long) total_rp * a.tiles_per_row;
+    unsigned long long g = (tiles + wpc - 1) / wpc;
+    if (g > (unsigned long long) sm_count) g = sm_count;
+    const unsigned W = (unsigned) g * wpc;
+    if (W >= (unsigned) a.tiles_per_row) {
+      grid = (unsigned) g;
+      a.lin_warps = (int) (W / a.tiles_per_row * a.tiles_per_row);
+      a.step_rp = (unsigned) a.lin_warps / a.tiles_per_row;
+      a.tile_stride = a.tiles_per_row;  // (the looping instantiation runs its loop once)
+    }
+  }
   const unsigned r2 = a.h / 2, d_f = a.step_rp / r2;
   a.d_rp = a.step_rp - d_f * r2;
   a.pi16 = (unsigned) (a.pi / 16); a.py4 = (unsigned) (a.py / 4); a.pc4 = (unsigned) (a.pc / 4);
@@ -343,7 +368,7 @@ static int launch_encode_fast1(const EncodeArgs &a0, int sm_count, cudaStream_t 
   const size_t smem = 65536 + ((size_t) (1 << a.out_cells_log2) + 1) * 32;
   // The looping instantiation is also valid for narrower rows (its loop runs once) and its code schedule measured
   // faster when all 32 warps have a tile (2048 wide: 905 vs 883 Gpix/s), slower with 30 (1920 wide: 881 vs 916).
-  const bool wide = a.tiles_per_row > wpc || wpc % a.tiles_per_row == 0;
+  const bool wide = a.tiles_per_row > wpc || wpc % a.tiles_per_row == 0 || a.lin_warps > 0;
   // calls of a few steps per warp (one or two frames) are launched with programmatic stream serialization
   const bool pdl = pdl_enabled((unsigned long long) total_rp <= 4ull * a.step_rp);
   cudaError_t le = cudaSuccess;

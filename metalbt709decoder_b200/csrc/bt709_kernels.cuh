@@ -90,6 +90,10 @@ struct EncodeArgs {
   int out_cells_log2;
   // fast kernel: band layout and 32-bit unit offsets (16 B for BGRA, 4 B for Y / CbCr), see k_encode_fast
   int tiles_per_row, rps, tile_stride;
+  // linear tile order (contiguous batches whose rows have fewer than 32 tiles and would leave warps idle in the band
+  // layout, e.g. 15 or 30 tiles for 1920 / 3840-wide rows): 0 = band layout, else the number of active warps of the grid,
+  // a multiple of tiles_per_row - warp g takes tile column g % tiles_per_row of row pairs g / tiles_per_row + k * step_rp
+  int lin_warps;
   unsigned step_rp, d_rp, pi16, py4, pc4, si16, sy4, sc4, di, dy, dc, wi, wy, wc;
   float one;  // 1.0f, deliberately a runtime value
   unsigned zero;  // 0, deliberately a runtime value (scheduling fence by data dependence, see k_encode_fast)

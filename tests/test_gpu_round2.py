@@ -695,3 +695,23 @@ print("variant ok")
     r = subprocess.run([sys.executable, "-c", code], cwd=ROOT, env=dict(os.environ, BT709_STRIDED_LIN="all"), capture_output=True,
                        text=True, timeout=600)
     assert r.returncode == 0 and "variant ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("w,h,F,gin,gout", [(1920, 1080, 3, 1, 0), (1280, 720, 5, 1, 1), (720, 480, 7, 2, 2), (3840, 64, 6, 1, 0),
+                                           (1920, 2, 40, 0, 0), (1440, 96, 9, 1, 0)])
+def test_encode_linear_tile_order(w, h, F, gin, gout):
+    """Rows of 15, 10, 6, 30 or 12 tiles would leave warps of a 32-warp CTA idle in the band layout; contiguous batches
+    take the tiles in linear order instead (k_encode_fast, EncodeArgs.lin_warps).  Every frame against the oracle."""
+    from _gpu import ctx, dev
+    srcs = [bgra_random(w, h, seed=1800 + f) for f in range(min(F, 4))]
+    tin = torch.stack([dev(srcs[f % len(srcs)]) for f in range(F)])
+    ey = torch.zeros((F, h, w), dtype=torch.uint8, device="cuda")
+    ec = torch.zeros((F, h // 2, w), dtype=torch.uint8, device="cuda")
+    n0 = ctx().launch_count
+    ctx().encode_bgra_to_nv12(gin, gout, tin, ey, ec, wait=True)
+    assert ctx().launch_count == n0 + 1
+    wants = [ORA.encode_bgra_nv12(gin, gout, s_) for s_ in srcs]
+    gy, gc = ey.cpu().numpy(), ec.cpu().numpy()
+    for f in range(F):
+        wy, wc = wants[f % len(srcs)]
+        assert np.array_equal(gy[f], wy) and np.array_equal(gc[f], wc), f"{w}x{h} frame {f}"
