@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(kPairWarps * 32, 1) k_rescale_pair(const Resca
   // Tile order: every tile that is not in the first or last tile column first, those two columns at the end.  The
   // walker has separate code for tiles without clamped taps (pair_tile: INNER), each variant a ~20 KB loop; with edge
   // tiles sprinkled through the order, one or two warps of every CTA sit in the other variant at any time and the
-  // instruction cache thrashes (measured: 288 against 327 Gpix/s).  (The variant itself is still chosen by a vote on
+  // instruction cache thrashes (measured: 288 against 316 Gpix/s).  (The variant itself is still chosen by a vote on
   // the real tap offsets: the order only decides WHEN a warp meets an edge tile.)
   const unsigned inner_x = tiles_x > 2 ? (unsigned) tiles_x - 2u : 0u, edge_x = (unsigned) tiles_x - inner_x;
   const unsigned n_inner = (unsigned) p.nframes * (unsigned) tiles_y * inner_x;
