@@ -224,9 +224,10 @@ def run_traffic_probe(args):
 
 
 # ------------------------------------------------------------------------- CPU reference
-def _cpu_decode_frames(gamma, w, h, nframes, threads):
+def _cpu_decode_frames(gamma, w, h, nframes, threads, keep=None):
     """Decode `nframes` synthetic 1080p-class frames with the reference's CPU code on `threads`
-    host threads (one frame per task).  Returns (seconds, kind)."""
+    host threads (one frame per task).  Returns (seconds, kind).  keep: a dict that receives the first frame's
+    input and CPU output (the parity check of the cpu_baseline leg compares the GPU's output with it)."""
     import ctypes
     import numpy as np
     sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -246,9 +247,11 @@ def _cpu_decode_frames(gamma, w, h, nframes, threads):
                 return
             y, c = frames[i % len(frames)]
             if kind == "reference":
-                impl.decode_nv12(gamma, y, c)
+                out = impl.decode_nv12(gamma, y, c)
             else:
-                impl.decode_nv12(gamma, y, c, nthreads=1)
+                out = impl.decode_nv12(gamma, y, c, nthreads=1)
+            if keep is not None and i == 0:
+                keep["y"], keep["c"], keep["out"] = y, c, out
 
     ths = [threading.Thread(target=work) for _ in range(threads)]
     t0 = time.perf_counter()
@@ -259,15 +262,27 @@ def _cpu_decode_frames(gamma, w, h, nframes, threads):
     return time.perf_counter() - t0, kind
 
 
-def cpu_baseline(gamma, w, h, budget_core_s=16.0):
+def cpu_baseline(gamma, w, h, budget_core_s=16.0, gpu_decode=None):
+    """The reference's CPU path timed on the host cores.  gpu_decode(y, c) -> (h, w, 4) uint8: when given, the GPU's output
+    for the first frame of the sample is compared with the CPU's (north_star: within 1 LSB, fraction of bit-exact
+    pixels reported) - the checker at work inside its own leg, not on the timed path."""
     cores = os.cpu_count() or 1
     # ~0.4 core-seconds per 1080p frame with a transfer curve, ~0.09 without (BASELINE.md §2)
     per_frame = (0.42 if gamma != 1 else 0.09) * (w * h) / (1920 * 1080)
     nframes = max(cores, int(budget_core_s * max(1, cores // 8) / per_frame))
     nframes = min(nframes, cores * 8)
-    secs, kind = _cpu_decode_frames(gamma, w, h, nframes, cores)
-    return {"value": nframes * w * h / secs / 1e9, "unit": "Gpix/s", "cores": cores, "kind": kind,
-            "sample": f"{nframes} synthetic {w}x{h} frames, one frame per task on {cores} host threads"}, secs
+    keep = {} if gpu_decode is not None else None
+    secs, kind = _cpu_decode_frames(gamma, w, h, nframes, cores, keep)
+    out = {"value": nframes * w * h / secs / 1e9, "unit": "Gpix/s", "cores": cores, "kind": kind,
+           "sample": f"{nframes} synthetic {w}x{h} frames, one frame per task on {cores} host threads"}
+    if keep:
+        import numpy as np
+        got = gpu_decode(keep["y"], keep["c"])
+        d = np.abs(got.astype(np.int16) - keep["out"].astype(np.int16))
+        out["parity"] = {"exact_fraction": float((d == 0).mean()), "max_abs_diff": int(d.max()), "pixels": int(w * h),
+                         "against": "the reference's BT709.h / sRGB.h compiled where they lie (oracle/_ref)" if kind == "reference"
+                                    else "oracle port", "what": "bt709_decode_nv12 output of the sample's first frame, all four channels"}
+    return out, secs
 
 
 def workload_text(name, frames, gamma_name):
@@ -424,6 +439,28 @@ def timed_steps(torch, ctx, step, stream, steps, device_index, lms=25):
     return e0.elapsed_time(e1) / 1e3, launches, clocks
 
 
+def encode_roundtrip_histogram(torch, ctx, w, h):
+    """north_star: "encode round-trip error reported as a histogram".  One frame of random colours, constant over each 2x2
+    block (so that the 4:2:0 subsampling loses nothing and what remains is the quantisation round trip, like the reference's
+    per-colour histograms, CoreImageMetalFilterTests.m:420-813): sRGB BGRA -> bt709_encode_bgra_to_nv12 (sRGB in, Apple
+    out) -> bt709_decode_nv12 (Apple curve) -> |difference| per B, G, R byte.  Device only, untimed."""
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1886)
+    blocks = torch.randint(0, 256, (1, h // 2, w // 2, 4), dtype=torch.uint8, device="cuda", generator=g)
+    src = blocks.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2).contiguous()
+    src[..., 3] = 255
+    y = torch.empty((1, h, w), dtype=torch.uint8, device="cuda")
+    c = torch.empty((1, h // 2, w), dtype=torch.uint8, device="cuda")
+    back = torch.empty((1, h, w, 4), dtype=torch.uint8, device="cuda")
+    ctx.encode_bgra_to_nv12(1, 0, src, y, c, wait=True)
+    ctx.decode_nv12(0, y, c, back, wait=True)
+    d = (back[..., :3].to(torch.int16) - src[..., :3].to(torch.int16)).abs().flatten()
+    hist = torch.bincount(d.to(torch.int64)).cpu().tolist()
+    return {"what": "abs difference per B,G,R byte after encode (sRGB->Apple 4:2:0) + decode (Apple->sRGB), 2x2-constant random colours",
+            "samples": int(d.numel()), "histogram": {str(i): int(n) for i, n in enumerate(hist) if n},
+            "max_abs_diff": len(hist) - 1}
+
+
 def run_extra_config(torch, ctx, name, gamma, gamma_name, device_index):
     """One of the other BASELINE configurations, timed in the same run, two ways: `value` is a short run after an idle
     gap (like the headline under the driver's --steps 20: the SM clock is still at its maximum), `sustained` is the same
@@ -452,6 +489,8 @@ def run_extra_config(torch, ctx, name, gamma, gamma_name, device_index):
     out = {"name": name, "workload": workload_text(name, frames, gamma_name), "value_basis": "input pixels", "warmup": 6}
     out.update(b)
     out["sustained"] = entry(sres[0], s_steps, sres[1], sres[2])
+    if kind == "encode":
+        out["roundtrip"] = encode_roundtrip_histogram(torch, ctx, w, h)
     del d
     torch.cuda.empty_cache()
     return out
@@ -555,7 +594,13 @@ def run_b200(args):
         launches_per_step = max(1, launches // max(1, args.steps))
         # DRAM traffic of the headline kernel from the counters, in this run (single GPU; outside the timed regions)
         live = live_traffic(args.workload, args.gamma, kind, w, h) if world == 1 and not args.no_live_traffic else None
-        cpu = cpu_baseline(gamma, w, h)[0] if world == 1 else None
+        def gpu_decode(y_np, c_np):
+            ty, tc = torch.from_numpy(y_np).cuda()[None], torch.from_numpy(c_np).cuda()[None]
+            o = torch.zeros((1, h, w, 4), dtype=torch.uint8, device="cuda")
+            ctx.decode_nv12(gamma, ty, tc, o, wait=True)
+            return o[0].cpu().numpy()
+
+        cpu = cpu_baseline(gamma, w, h, gpu_decode=gpu_decode if kind == "decode" else None)[0] if world == 1 else None
         line = {
             "metric": "Gpix/s BT.709 4:2:0->sRGB BGRA8", "value": all_units / secs / 1e9, "unit": "Gpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": secs / args.steps * 1e3,
