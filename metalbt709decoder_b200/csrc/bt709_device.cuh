@@ -195,7 +195,13 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), unsigned grid, un
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, kernel, args...);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  if (pdl && e == cudaErrorNotSupported) {  // a driver / partition without programmatic launch: plain stream order
+    (void) cudaGetLastError();
+    cfg.numAttrs = 0;
+    e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  }
+  return e;
 }
 // BT709_PDL=0: never; BT709_PDL=all: every launch that supports it; default: small calls only
 static inline bool pdl_enabled(bool small_call) {
