@@ -45,6 +45,11 @@ struct bt709_ctx {
   const uint32_t *fl_lut[3] = {};
   float fl_clamp[3] = {};
   int fl_cells[3] = {};
+  // biased log-cell form of the same step functions (optional: the 4:2:0 encode's chroma lookup, one replica per lane)
+  const uint32_t *fl_blog_lut[3] = {};
+  float fl_blog_clamp[3] = {}, fl_blog_bias[3] = {};
+  int fl_blog_cells[3] = {};
+  unsigned fl_blog_first[3] = {};
   const float *lin256[3] = {};       // BT709_tolinearNorm per input gamma
   const float *compn256[3][3] = {};  // [gin][gout] unorm8(from_linear(to_linear(b)))
   // per-pixel 4:4:4 encoders: sRGB byte -> non-linear value fed to the matrix, per bt709_gamma
@@ -132,7 +137,7 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
 
   // ---- build every table on the host, once
   BlobBuilder blob;
-  size_t off_dec[5], off_fl[3], off_lin[3], off_comp[3][3], off_e444[5] = {}, off_log = 0, off_blog = 0;
+  size_t off_dec[5], off_fl[3], off_lin[3], off_comp[3][3], off_e444[5] = {}, off_log = 0, off_blog = 0, off_flb[3] = {};
   for (int g = 0; g < 5; g++) {
     StepFn fn;
     CellLut lut;
@@ -170,6 +175,14 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
     ctx->fl_clamp[g] = lut.clamp_lo;
     ctx->fl_cells[g] = n;
     off_fl[g] = blob.add(lut.entries.data(), lut.entries.size());
+    BiasedLogLut fb;
+    if (n > 8 && build_biased_log_lut(fn, 1.0f / 32.0f, &fb)) {  // steep curves only (Apple, sRGB): 645 cells instead of 4096
+      ctx->fl_blog_clamp[g] = fb.clamp_lo;
+      ctx->fl_blog_bias[g] = fb.bias;
+      ctx->fl_blog_cells[g] = (int) fb.entries.size();
+      ctx->fl_blog_first[g] = fb.first;
+      off_flb[g] = blob.add(fb.entries.data(), fb.entries.size());
+    }
     float lin[256];
     for (int b = 0; b < 256; b++) lin[b] = to_linear(g, b);
     off_lin[g] = blob.add(lin, 256);
@@ -202,6 +215,7 @@ int bt709_ctx_create(int device, bt709_ctx **out) {
   if (ctx->dec_blog_cells) ctx->dec_blog_lut = base + off_blog;
   for (int g = 0; g < 3; g++) {
     ctx->fl_lut[g] = base + off_fl[g];
+    if (ctx->fl_blog_cells[g] > 0) ctx->fl_blog_lut[g] = base + off_flb[g];
     ctx->lin256[g] = (const float *) (base + off_lin[g]);
     for (int go = 0; go < 3; go++) ctx->compn256[g][go] = (const float *) (base + off_comp[g][go]);
   }
@@ -423,6 +437,8 @@ int bt709_encode_bgra_to_nv12(const bt709_ctx *ctx, bt709_gamma gin, bt709_gamma
   a.lin256 = ctx->lin256[gin];
   a.compn256 = ctx->compn256[gin][gout];
   a.out_lut = ctx->fl_lut[gout]; a.out_clamp_lo = ctx->fl_clamp[gout]; a.out_cells_log2 = ctx->fl_cells[gout];
+  a.out_blog_lut = ctx->fl_blog_lut[gout]; a.out_blog_clamp_lo = ctx->fl_blog_clamp[gout]; a.out_blog_bias = ctx->fl_blog_bias[gout];
+  a.out_blog_cells = ctx->fl_blog_cells[gout]; a.out_blog_first = ctx->fl_blog_first[gout];
   const unsigned long long l0 = launches_begin();
   return finish(ctx, l0, launch_encode(a, ctx->sm_count, stream), stream, wait);
 }

@@ -130,13 +130,19 @@ __device__ __forceinline__ f32x2 add2_nc(f32x2 a, f32x2 b, const EncK &k) { retu
 
 // FULL = (w % 128 == 0): no per-lane predicates; otherwise the lanes past the row end load nothing and store nothing
 // WIDE: rows of more than 32 tiles (4096 pixels): the warps loop over the tile columns, 32 apart
-template <bool WRAP, bool FULL, bool WIDE>
+// OMODE: form of the chroma LUT (BT709_from_linear as a cell LUT).  ncu on 385 x 1080p (session 54): 30 shared loads per
+// warp-step but 65.9 shared wavefronts, 11.9 of them bank conflicts - all in the six chroma lookups, whose 4096-cell
+// uniform LUT only fits with 8 replicas (random means: ~3 wavefronts per lookup), on a kernel that keeps the L1 / shared
+// pipe 96.7 % busy.  0: uniform cells, 8 replicas (the fallback); 1: uniform cells, one replica per lane (curves that need
+// <= 256 cells: the Linear output); 2: biased log cells (645 for the Apple and sRGB curves), one replica per lane - one
+// PRMT more per lookup, no conflicts for any content.
+template <bool WRAP, bool FULL, bool WIDE, int OMODE>
 __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
   // [0, 64 KB): float2 table, entry b replica r at byte b*256 + r*8;  then the chroma cell LUT
   float2 *s_tab = reinterpret_cast<float2 *>(s_mem);
   uint32_t *s_olut = s_mem + 256 * 64;
-  const int nl = (1 << p.out_cells_log2) + 1;
+  const int nl = OMODE == 2 ? p.out_blog_cells : (1 << p.out_cells_log2) + 1;
   pdl_launch_dependents();
   // every table entry is read from global memory once and its replicas are written with 16-byte stores (the old
   // loops read an entry once per replica: ~10 dependent L2 round trips per thread, a third of a one-frame call)
@@ -144,9 +150,9 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
     const float l = __ldg(&p.lin256[b]), cn = __ldg(&p.compn256[b]);
     reinterpret_cast<float4 *>(s_tab + b * 32)[threadIdx.x & 15] = make_float4(l, cn, l, cn);
   }
-  // chroma cell LUT replicated 8x (entry i replica r at word i*8 + r): random means otherwise
-  // cost ~3 wavefronts per lookup and the kernel is bound by shared-memory bandwidth
-  fill_replicated<3>(s_olut, 8, p.out_lut, nl);
+  // chroma cell LUT: entry i replica r at word i*R + r (R = 8 or 32, see OMODE)
+  if (OMODE == 0) fill_replicated<3>(s_olut, 8, p.out_lut, nl);
+  else fill_replicated<5>(s_olut, 32, OMODE == 2 ? p.out_blog_lut : p.out_lut, nl);
   __syncthreads();
   pdl_wait();  // small calls are launched with programmatic stream serialization: the tables above are constant
 
@@ -154,8 +160,13 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   const unsigned warp = threadIdx.x >> 5;
   const uint32_t tab = (uint32_t) __cvta_generic_to_shared(s_tab);  // warp-uniform
   const uint32_t lane8 = lane << 3;
-  const uint32_t olut = (uint32_t) __cvta_generic_to_shared(s_olut) + ((lane & 7) << 2) - (0x4B000000u << 5);
-  const float clamp_lo = p.out_clamp_lo;
+  // lookup base: replica of this lane, minus the bias of the index register (2^23 magic for uniform cells, the first
+  // cell for log cells), so that a lookup address is (index register << shift) + olut
+  const uint32_t olut = (uint32_t) __cvta_generic_to_shared(s_olut) +
+                        (OMODE == 0 ? ((lane & 7) << 2) - (0x4B000000u << 5)
+                                    : (lane << 2) - ((OMODE == 2 ? p.out_blog_first : 0x4B000000u) << 7));
+  const float clamp_lo = OMODE == 2 ? p.out_blog_clamp_lo : p.out_clamp_lo;
+  const float obias = p.out_blog_bias;
   const float fN = (float) (1 << p.out_cells_log2);
   EncK k;
   auto bc = [](float v) { return pk(v, v); };
@@ -192,9 +203,14 @@ __global__ void __launch_bounds__(1024, 1) k_encode_fast(const EncodeArgs p) {
   };
   auto code_of = [&](float mean) -> float {  // BT709_from_linear code as a magic float 2^23 + code
     float xc = fmaxf(mean, clamp_lo), t;
-    asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(t) : "f"(xc), "f"(fN));
     uint32_t e;
-    asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((__float_as_uint(t) << 5) + olut));
+    if (OMODE == 2) {  // cell of xc + bias: the upper half of the float (PRMT, not a shift: see lut2 in bt709_decode_row.cuh)
+      const uint32_t cell = __byte_perm(__float_as_uint(__fadd_rn(xc, obias)), 0, 0x4432);
+      asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((cell << 7) + olut));
+    } else {
+      asm("fma.rz.f32 %0, %1, %2, 0f4B000000;" : "=f"(t) : "f"(xc), "f"(fN));
+      asm("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"((__float_as_uint(t) << (OMODE ? 7 : 5)) + olut));
+    }
     return __uint_as_float(__byte_perm(e + __float_as_uint(xc), 0x4B000000u, 0x7543));
   };
 
@@ -365,17 +381,33 @@ static int launch_encode_fast1(const EncodeArgs &a0, int sm_count, cudaStream_t 
   a.wi = a.si16 - r2 * 2 * a.pi16; a.wy = a.sy4 - r2 * 2 * a.py4; a.wc = a.sc4 - r2 * a.pc4;
   a.one = 1.0f;
   a.zero = 0;
-  const size_t smem = 65536 + ((size_t) (1 << a.out_cells_log2) + 1) * 32;
+  // chroma LUT form (see k_encode_fast): biased log cells with a replica per lane when the context has them and they fit,
+  // else uniform cells with a replica per lane when the curve needs <= 256 of them, else uniform cells with 8 replicas.
+  // BT709_ENC_OMODE=0|1|2 forces a form that is available (reproduction).
+  static const char *omode_env = getenv("BT709_ENC_OMODE");
+  int omode = 0;
+  if (a.out_blog_lut && a.out_blog_cells > 0 && 65536 + (size_t) a.out_blog_cells * 128 <= kMaxDynSmem) omode = 2;
+  else if (a.out_cells_log2 <= 8) omode = 1;
+  if (omode_env) {
+    const int want = atoi(omode_env);
+    if (want == 0 || (want == 1 && a.out_cells_log2 <= 8) || (want == 2 && omode == 2)) omode = want;
+  }
+  const size_t smem = 65536 + (omode == 2 ? (size_t) a.out_blog_cells * 128
+                                          : ((size_t) (1 << a.out_cells_log2) + 1) * (omode == 1 ? 128 : 32));
   // The looping instantiation is also valid for narrower rows (its loop runs once) and its code schedule measured
   // faster when all 32 warps have a tile (2048 wide: 905 vs 883 Gpix/s), slower with 30 (1920 wide: 881 vs 916).
   const bool wide = a.tiles_per_row > wpc || wpc % a.tiles_per_row == 0 || a.lin_warps > 0;
   // calls of a few steps per warp (one or two frames) are launched with programmatic stream serialization
   const bool pdl = pdl_enabled((unsigned long long) total_rp <= 4ull * a.step_rp);
   cudaError_t le = cudaSuccess;
+#define BT709_ENC_LAUNCH1(W, F, X, O) le = launch_pdl(k_encode_fast<W, F, X, O>, grid, 1024, smem, s, pdl, a), note_launch()
 #define BT709_ENC_LAUNCH(W, F)                                                      \
   do {                                                                              \
-    if (wide) le = launch_pdl(k_encode_fast<W, F, true>, grid, 1024, smem, s, pdl, a), note_launch();   \
-    else le = launch_pdl(k_encode_fast<W, F, false>, grid, 1024, smem, s, pdl, a), note_launch();        \
+    if (wide) {                                                                     \
+      if (omode == 2) BT709_ENC_LAUNCH1(W, F, true, 2); else if (omode == 1) BT709_ENC_LAUNCH1(W, F, true, 1); else BT709_ENC_LAUNCH1(W, F, true, 0);    \
+    } else {                                                                        \
+      if (omode == 2) BT709_ENC_LAUNCH1(W, F, false, 2); else if (omode == 1) BT709_ENC_LAUNCH1(W, F, false, 1); else BT709_ENC_LAUNCH1(W, F, false, 0); \
+    }                                                                               \
   } while (0)
   if (wrap) {
     if (full) BT709_ENC_LAUNCH(true, true); else BT709_ENC_LAUNCH(true, false);
@@ -383,6 +415,7 @@ static int launch_encode_fast1(const EncodeArgs &a0, int sm_count, cudaStream_t 
     if (full) BT709_ENC_LAUNCH(false, true); else BT709_ENC_LAUNCH(false, false);
   }
 #undef BT709_ENC_LAUNCH
+#undef BT709_ENC_LAUNCH1
   if (le != cudaSuccess) return (int) le;
   return (int) cudaGetLastError();
 }
@@ -411,12 +444,19 @@ int launch_encode(const EncodeArgs &a, int sm_count, void *stream) {
   return (int) cudaGetLastError();
 }
 
+template <bool W, bool F, bool X, int O>
+static int optin_encode_smem1() {
+  return (int) cudaFuncSetAttribute(k_encode_fast<W, F, X, O>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kMaxDynSmem);
+}
 template <bool W, bool F>
 static int optin_encode_smem() {
-  const int smem = 65536 + 4097 * 32;
-  int e = (int) cudaFuncSetAttribute(k_encode_fast<W, F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  if (e) return e;
-  return (int) cudaFuncSetAttribute(k_encode_fast<W, F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  int e;
+  if ((e = optin_encode_smem1<W, F, false, 0>())) return e;
+  if ((e = optin_encode_smem1<W, F, false, 1>())) return e;
+  if ((e = optin_encode_smem1<W, F, false, 2>())) return e;
+  if ((e = optin_encode_smem1<W, F, true, 0>())) return e;
+  if ((e = optin_encode_smem1<W, F, true, 1>())) return e;
+  return optin_encode_smem1<W, F, true, 2>();
 }
 
 int encode_kernels_init() {

@@ -88,6 +88,12 @@ struct EncodeArgs {
   const uint32_t *out_lut;  // linear float -> output-gamma byte (cell LUT, BT709_from_linear)
   float out_clamp_lo;
   int out_cells_log2;
+  // optional biased log-cell form of the same step function (bt709_tables.h: BiasedLogLut): ~645 cells for the Apple and
+  // sRGB curves instead of 4096 uniform ones, so one replica per lane fits shared memory (k_encode_fast: OMODE 2)
+  const uint32_t *out_blog_lut;
+  float out_blog_clamp_lo, out_blog_bias;
+  int out_blog_cells;
+  unsigned out_blog_first;
   // fast kernel: band layout and 32-bit unit offsets (16 B for BGRA, 4 B for Y / CbCr), see k_encode_fast
   int tiles_per_row, rps, tile_stride;
   // linear tile order (contiguous batches whose rows have fewer than 32 tiles and would leave warps idle in the band

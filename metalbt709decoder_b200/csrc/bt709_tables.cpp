@@ -327,10 +327,14 @@ int selftest_host() {
   // 1b. biased log-cell LUT of the sRGB encode (pass 2, fused kernel, Linear-mode decode) == the step function:
   //     every float within 64 ulp of a threshold or of a cell boundary, and 4 M floats spread over [0, 1]
   //     (the exhaustive sweep over all 1.07e9 floats of [0, 1] was run once at development time: 0 mismatches)
-  {
+  //     - and the same for the biased log-cell LUTs of BT709_from_linear (Apple and sRGB curves), which the 4:2:0
+  //     encode's chroma lookup uses with one replica per lane (k_encode_fast, OMODE 2)
+  struct BlogCase { CodeFn fn; int mode; };
+  const BlogCase blog_cases[] = {{decode_code, kLinear}, {from_linear_code, kApple}, {from_linear_code, kSrgb}};
+  for (const BlogCase &bc : blog_cases) {
     StepFn fn;
     BiasedLogLut bl;
-    if (!build_step_fn(decode_code, kLinear, &fn)) return 1;
+    if (!build_step_fn(bc.fn, bc.mode, &fn)) return 1;
     if (!build_biased_log_lut(fn, 1.0f / 32.0f, &bl)) return 10;
     long bad = 0;
     auto check = [&](uint32_t bits) {
