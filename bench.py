@@ -161,6 +161,22 @@ _KERNELS_OF = {"decode": "k_decode", "alpha": "k_decode", "rescale": "k_rescale"
                "twopass": "k_decode|k_rescale"}
 
 
+def parse_ncu_dram_bytes(csv_path):
+    """(sum of dram__bytes_read.sum + dram__bytes_write.sum in bytes, number of counter rows) of an `ncu --csv` log"""
+    import csv
+    rows = [x for x in csv.reader(open(csv_path)) if len(x) > 10]
+    if not rows:
+        return 0.0, 0
+    ix = {n: i for i, n in enumerate(rows[0])}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, 0
+    for x in rows[1:]:
+        if x[ix["Metric Name"]] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            total += float(x[ix["Metric Value"]].replace(",", "")) * scale[x[ix["Metric Unit"]]]
+            seen += 1
+    return total, seen
+
+
 def live_traffic(workload, gamma_name, kind, w, h):
     """DRAM bytes per pixel of this workload's kernel(s), read from the hardware counters IN THIS RUN: a child process
     (`bench.py --traffic-probe`, three untimed steps of the same workload on a batch still far larger than L2) runs under
@@ -184,15 +200,7 @@ def live_traffic(workload, gamma_name, kind, w, h):
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=180)
         if r.returncode != 0:
             return None, "ncu probe failed (rc %d)" % r.returncode
-        import csv
-        rows = [x for x in csv.reader(open(log)) if len(x) > 10]
-        ix = {n: i for i, n in enumerate(rows[0])}
-        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
-        total, seen = 0.0, 0
-        for x in rows[1:]:
-            if x[ix["Metric Name"]] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                total += float(x[ix["Metric Value"]].replace(",", "")) * scale[x[ix["Metric Unit"]]]
-                seen += 1
+        total, seen = parse_ncu_dram_bytes(log)
         if seen != 2 * per_step:
             return None, "ncu probe captured %d of %d counters" % (seen, 2 * per_step)
         return total / (float(frames) * w * h), ("dram__bytes_read.sum + dram__bytes_write.sum read by ncu in this run (child process, "
